@@ -1,0 +1,139 @@
+"""Host-side camera algebra feeding GaussianRasterizationSettings.
+
+Mirrors the two camera classes of the reference so callers can switch unchanged:
+
+* ``Camera``  — gaussiansplatting/scene/cameras.py:17-51 (c2w in OpenGL/NeRF convention,
+  ``world_view_transform = (flip . c2w^-1)^T``, ``full_proj_transform = view @ proj``,
+  ``camera_center = view^-1[3, :3]``; znear 0.01 / zfar 100).
+* ``MiniCam`` — gs_renderer.py:853-879 (same flip; ``camera_center = -c2w[:3, 3]`` as the
+  reference does, which is what its SH evaluation sees).
+
+Difference by design: the 4x4 algebra is done on the HOST in float64 and
+uploaded once, instead of two ``torch.inverse`` launches on the GPU per view; ``tanfovx`` /
+``tanfovy`` are plain Python floats, so building settings never synchronises the device.
+Matrices keep the reference's row-vector convention: the flat memory is the column-major
+world->view matrix, ``x_view = m[0]*x + m[4]*y + m[8]*z + m[12]``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+
+def fov2focal(fov: float, pixels: int) -> float:
+    """gaussiansplatting/utils/graphics_utils.py:95-96."""
+    return pixels / (2.0 * math.tan(fov / 2.0))
+
+
+def focal2fov(focal: float, pixels: int) -> float:
+    """gaussiansplatting/utils/graphics_utils.py:98-99."""
+    return 2.0 * math.atan(pixels / (2.0 * focal))
+
+
+def projection_matrix(znear: float, zfar: float, fovx: float, fovy: float) -> np.ndarray:
+    """Perspective matrix of graphics_utils.py:73-93 (symmetric frustum, z_sign = +1)."""
+    P = np.zeros((4, 4), dtype=np.float64)
+    P[0, 0] = 1.0 / math.tan(fovx / 2.0)
+    P[1, 1] = 1.0 / math.tan(fovy / 2.0)
+    P[3, 2] = 1.0
+    P[2, 2] = zfar / (zfar - znear)
+    P[2, 3] = -(zfar * znear) / (zfar - znear)
+    return P
+
+
+def _w2c_from_c2w(c2w) -> np.ndarray:
+    c2w = np.asarray(c2w.detach().cpu() if torch.is_tensor(c2w) else c2w, dtype=np.float64)
+    w2c = np.linalg.inv(c2w)
+    w2c[1:3, :3] *= -1.0          # OpenGL -> COLMAP axis flip ("rectify", cameras.py:25-27)
+    w2c[:3, 3] *= -1.0
+    return w2c
+
+
+class Camera:
+    """Drop-in for gaussiansplatting.scene.cameras.Camera (cameras.py:17-51)."""
+
+    def __init__(self, c2w, FoVy, height, width, trans=None, scale=1.0, data_device="cuda"):
+        FoVy = float(FoVy)
+        self.FoVx = focal2fov(fov2focal(FoVy, height), width)
+        self.FoVy = FoVy
+        self.image_height = int(height)
+        self.image_width = int(width)
+        self.zfar = 100.0
+        self.znear = 0.01
+        self.trans = torch.zeros(3) if trans is None else trans.float()
+        self.scale = scale
+        self.data_device = torch.device(data_device)
+        w2c = _w2c_from_c2w(c2w)
+        view = w2c.T
+        proj = projection_matrix(self.znear, self.zfar, self.FoVx, self.FoVy).T
+        full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
+        center = np.linalg.inv(view)[3, :3]
+        dev = self.data_device
+        self.world_view_transform = torch.tensor(view, dtype=torch.float32).to(dev)
+        self.projection_matrix = torch.tensor(proj, dtype=torch.float32).to(dev)
+        self.full_proj_transform = torch.tensor(full, dtype=torch.float32).to(dev)
+        self.camera_center = torch.tensor(center, dtype=torch.float32).to(dev)
+
+    @property
+    def tanfovx(self) -> float:
+        return math.tan(self.FoVx * 0.5)
+
+    @property
+    def tanfovy(self) -> float:
+        return math.tan(self.FoVy * 0.5)
+
+
+class MiniCam:
+    """Drop-in for gs_renderer.MiniCam (gs_renderer.py:853-879)."""
+
+    def __init__(self, c2w, width, height, fovy, fovx, znear, zfar, data_device="cuda"):
+        self.image_width = int(width)
+        self.image_height = int(height)
+        self.FoVy = float(fovy)
+        self.FoVx = float(fovx)
+        self.znear = znear
+        self.zfar = zfar
+        c2w = np.asarray(c2w, dtype=np.float64)
+        w2c = _w2c_from_c2w(c2w)
+        view = w2c.T
+        proj = projection_matrix(znear, zfar, self.FoVx, self.FoVy).T
+        full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
+        dev = torch.device(data_device)
+        self.world_view_transform = torch.tensor(view, dtype=torch.float32).to(dev)
+        self.projection_matrix = torch.tensor(proj, dtype=torch.float32).to(dev)
+        self.full_proj_transform = torch.tensor(full, dtype=torch.float32).to(dev)
+        self.camera_center = -torch.tensor(c2w[:3, 3], dtype=torch.float32).to(dev)
+
+    @property
+    def tanfovx(self) -> float:
+        return math.tan(self.FoVx * 0.5)
+
+    @property
+    def tanfovy(self) -> float:
+        return math.tan(self.FoVy * 0.5)
+
+
+def look_at_c2w(position, center=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0)) -> np.ndarray:
+    """c2w of a camera at ``position`` looking at ``center``, built as the reference's
+    random-camera collate does (threestudio/data/camera_data.py:444-454):
+    columns = right, up, -lookat, position."""
+    position = np.asarray(position, dtype=np.float64)
+    look = np.asarray(center, dtype=np.float64) - position
+    look /= np.linalg.norm(look)
+    right = np.cross(look, np.asarray(up, dtype=np.float64))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, look)
+    upv /= np.linalg.norm(upv)
+    c2w = np.eye(4)
+    c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, upv, -look, position
+    return c2w
+
+
+def orbit_position(azimuth_deg: float, elevation_deg: float, distance: float) -> np.ndarray:
+    """z-up orbit position (camera_data.py:356-364)."""
+    az, el = math.radians(azimuth_deg), math.radians(elevation_deg)
+    return np.array([distance * math.cos(el) * math.cos(az),
+                     distance * math.cos(el) * math.sin(az),
+                     distance * math.sin(el)])
