@@ -1,0 +1,271 @@
+// extern "C" surface of libgsb.so (include/gsb.h): argument validation, workspace layout,
+// stage chaining on the caller's stream.  No torch types, no allocation, no exceptions.
+#include <stdio.h>
+#include <string.h>
+
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+static thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return GSB_E_CUDA;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static bool settings_ok(const GsbSettings* s) {
+  return s && s->image_height > 0 && s->image_width > 0 && s->sh_degree >= 0 && s->sh_degree <= 3 && s->bg &&
+         s->viewmatrix && s->projmatrix && s->campos && s->tanfovx > 0.f && s->tanfovy > 0.f &&
+         s->image_width <= 65535 * TILE_X && s->image_height <= 65535 * TILE_Y;
+}
+
+static int layout(int P, int H, int W, long long D_cap, GsbLayout* L) {
+  if (P < 0 || H <= 0 || W <= 0 || D_cap < 0 || !L) return GSB_E_INVALID;
+  if (D_cap > 0xFFFFFFF0ll) return GSB_E_UNSUPPORTED;
+  memset(L, 0, sizeof(*L));
+  const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  const size_t HW = (size_t)H * W, Pz = (size_t)P, Dz = (size_t)D_cap;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  L->off_geom = take(Pz * sizeof(Geom));
+  L->off_clamped = take(Pz);
+  L->off_counts = take(8 * sizeof(uint32_t));
+  L->off_point_list = take(Dz * 4);
+  L->off_ranges = take(T * sizeof(uint2));
+  L->off_n_contrib = take(HW * 4);
+  L->off_final_T = take(HW * 4);
+  L->saved_bytes = o;
+  o = 0;
+  L->off_rect = take(Pz * 8);
+  L->off_tiles = take(Pz * 4);
+  L->off_dkeys0 = take(Pz * 4);
+  L->off_dkeys1 = take(Pz * 4);
+  L->off_dkeys2 = take(Pz * 4);
+  L->off_didx0 = take(Pz * 4);
+  L->off_didx1 = take(Pz * 4);
+  L->off_offsets = take(Pz * 4);
+  L->off_blocksums = take((Pz / 2048 + 2) * 4);
+  const size_t nmax = Dz > Pz ? Dz : Pz;
+  L->off_hist = take(radix_tmp_bytes((long long)nmax));
+  L->off_tkeys0 = take(Dz * 4);
+  L->off_tkeys1 = take(Dz * 4);
+  L->off_tvals_alt = take(Dz * 4);
+  L->off_keys64_0 = take(Dz * 8);
+  L->off_keys64_1 = take(Dz * 8);
+  L->off_ggrad = take(Pz * sizeof(GGrad));
+  L->scratch_bytes = o;
+  return GSB_OK;
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+
+const char* gsb_strerror(int code) {
+  switch (code) {
+    case GSB_OK: return "ok";
+    case GSB_E_INVALID: return "invalid argument";
+    case GSB_E_CUDA: return "CUDA error";
+    case GSB_E_CAPACITY: return "instance capacity exceeded";
+    case GSB_E_UNSUPPORTED: return "unsupported size";
+    default: return "unknown error";
+  }
+}
+
+const char* gsb_last_cuda_error(void) { return g_cuda_err; }
+
+int gsb_layout(int P, int H, int W, long long D_cap, GsbLayout* out) { return layout(P, H, W, D_cap, out); }
+
+int gsb_preprocess_fwd(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
+                       const float* rotations, const float* opacities, const float* shs,
+                       const float* colors_precomp, const float* cov3D_precomp, int32_t* radii_out,
+                       void* saved, void* scratch, long long D_cap, void* stream) {
+  if (!settings_ok(s) || P < 0) return GSB_E_INVALID;
+  if (P == 0) return GSB_OK;
+  if (!means3D || !opacities || !radii_out || !saved || !scratch) return GSB_E_INVALID;
+  if ((shs != nullptr) == (colors_precomp != nullptr)) return GSB_E_INVALID;
+  if ((cov3D_precomp != nullptr) == (scales != nullptr && rotations != nullptr)) return GSB_E_INVALID;
+  if (shs && K < (s->sh_degree + 1) * (s->sh_degree + 1)) return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
+  if (rc) return rc;
+  const View v = make_view(s);
+  return launch_preprocess_fwd(v, P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
+                               cov3D_precomp, radii_out, at<Geom>(saved, L.off_geom),
+                               at<uint8_t>(saved, L.off_clamped), at<ushort4>(scratch, L.off_rect),
+                               at<uint32_t>(scratch, L.off_tiles), at<uint32_t>(scratch, L.off_dkeys0),
+                               at<uint32_t>(saved, L.off_counts), s->debug != 0, (cudaStream_t)stream);
+}
+
+int gsb_bin_sort(const GsbSettings* s, int P, void* saved, void* scratch, long long D_cap, int mode,
+                 uint32_t* host_counts, void* event, void* stream) {
+  if (!settings_ok(s) || P < 0 || !saved || !scratch) return GSB_E_INVALID;
+  if (mode != GSB_BIN_TWO_LEVEL && mode != GSB_BIN_FLAT64) return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
+  if (rc) return rc;
+  return launch_bin_sort(make_view(s), P, saved, scratch, L, D_cap, mode, host_counts, (cudaEvent_t)event,
+                         s->debug != 0, (cudaStream_t)stream);
+}
+
+int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap, float* out_color,
+                   float* out_depth, float* out_alpha, void* stream) {
+  if (!settings_ok(s) || P < 0 || !saved || !out_color || !out_depth || !out_alpha) return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
+  if (rc) return rc;
+  return launch_render_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
+                           at<uint2>(saved, L.off_ranges), out_color, out_depth, out_alpha,
+                           at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
+                           (cudaStream_t)stream);
+}
+
+int gsb_forward(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
+                const float* rotations, const float* opacities, const float* shs,
+                const float* colors_precomp, const float* cov3D_precomp, int32_t* radii_out,
+                float* out_color, float* out_depth, float* out_alpha, void* saved, void* scratch,
+                long long D_cap, int mode, uint32_t* host_counts, void* event, void* stream) {
+  int rc = gsb_preprocess_fwd(s, P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
+                              cov3D_precomp, radii_out, saved, scratch, D_cap, stream);
+  if (rc) return rc;
+  rc = gsb_bin_sort(s, P, saved, scratch, D_cap, mode, host_counts, event, stream);
+  if (rc) return rc;
+  return gsb_render_fwd(s, P, saved, D_cap, out_color, out_depth, out_alpha, stream);
+}
+
+int gsb_read_counts(const void* saved, int P, int H, int W, long long D_cap, uint32_t* host_dst,
+                    void* stream) {
+  if (!saved || !host_dst) return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, H, W, D_cap, &L);
+  if (rc) return rc;
+  GSB_CUDA(cudaMemcpyAsync(host_dst, at<uint32_t>(saved, L.off_counts), 8 * sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return GSB_OK;
+}
+
+int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch, long long D_cap,
+                   const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, void* stream) {
+  if (!settings_ok(s) || P < 0 || !saved || !scratch || !dL_dcolor || !dL_ddepth || !dL_dalpha)
+    return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
+  if (rc) return rc;
+  return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
+                           at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_n_contrib),
+                           at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
+                           at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
+}
+
+int gsb_preprocess_bwd(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
+                       const float* rotations, const float* opacities, const float* shs,
+                       const float* colors_precomp, const float* cov3D_precomp, const int32_t* radii,
+                       const void* saved, const void* scratch, long long D_cap, float* dL_dmeans3D,
+                       float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors, float* dL_dopacities,
+                       float* dL_dscales, float* dL_drotations, float* dL_dcov3D, int accumulate,
+                       void* stream) {
+  if (!settings_ok(s) || P < 0) return GSB_E_INVALID;
+  if (P == 0) return GSB_OK;
+  if (!means3D || !radii || !saved || !scratch || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacities)
+    return GSB_E_INVALID;
+  if ((shs != nullptr) == (colors_precomp != nullptr)) return GSB_E_INVALID;
+  if ((cov3D_precomp != nullptr) == (scales != nullptr && rotations != nullptr)) return GSB_E_INVALID;
+  if (shs && !dL_dshs) return GSB_E_INVALID;
+  if (colors_precomp && !dL_dcolors) return GSB_E_INVALID;
+  if (cov3D_precomp && !dL_dcov3D) return GSB_E_INVALID;
+  if (!cov3D_precomp && (!dL_dscales || !dL_drotations)) return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
+  if (rc) return rc;
+  return launch_preprocess_bwd(make_view(s), P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
+                               cov3D_precomp, radii, at<Geom>(saved, L.off_geom),
+                               at<uint8_t>(saved, L.off_clamped), at<GGrad>(scratch, L.off_ggrad), dL_dmeans3D,
+                               dL_dmeans2D, shs ? dL_dshs : nullptr, colors_precomp ? dL_dcolors : nullptr,
+                               dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, accumulate, s->debug != 0,
+                               (cudaStream_t)stream);
+}
+
+int gsb_backward(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
+                 const float* rotations, const float* opacities, const float* shs,
+                 const float* colors_precomp, const float* cov3D_precomp, const int32_t* radii,
+                 const void* saved, void* scratch, long long D_cap, const float* dL_dcolor,
+                 const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D,
+                 float* dL_dshs, float* dL_dcolors, float* dL_dopacities, float* dL_dscales,
+                 float* dL_drotations, float* dL_dcov3D, int accumulate, void* stream) {
+  int rc = gsb_render_bwd(s, P, saved, scratch, D_cap, dL_dcolor, dL_ddepth, dL_dalpha, stream);
+  if (rc) return rc;
+  return gsb_preprocess_bwd(s, P, K, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp,
+                            radii, saved, scratch, D_cap, dL_dmeans3D, dL_dmeans2D, dL_dshs, dL_dcolors,
+                            dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, accumulate, stream);
+}
+
+int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return GSB_E_INVALID;
+  return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int gsb_debug_sorted_keys(int P, int H, int W, const void* saved, const void* scratch, long long D_cap,
+                          uint64_t* keys_out, void* stream) {
+  if (!saved || !scratch || !keys_out) return GSB_E_INVALID;
+  GsbLayout L;
+  int rc = layout(P, H, W, D_cap, &L);
+  if (rc) return rc;
+  View v;
+  memset(&v, 0, sizeof(v));
+  v.H = H; v.W = W; v.gx = (W + TILE_X - 1) / TILE_X; v.gy = (H + TILE_Y - 1) / TILE_Y;
+  return launch_debug_sorted_keys(v, P, saved, scratch, L, D_cap, keys_out, (cudaStream_t)stream);
+}
+
+size_t gsb_radix_tmp_bytes(long long n, int key_bytes) {
+  if (n < 0) return 0;
+  const size_t nz = (size_t)n;
+  // ping-pong key+value buffers (A and B) followed by the histogram block
+  return 2 * (align_up(nz * (size_t)key_bytes) + align_up(nz * 4)) + align_up(radix_tmp_bytes(n));
+}
+
+static int radix_entry(long long n, const void* keys_in, const uint32_t* vals_in, void* keys_out,
+                       uint32_t* vals_out, int end_bit, void* tmp, void* stream, int key_bytes) {
+  if (n < 0 || end_bit < 0 || end_bit > key_bytes * 8) return GSB_E_INVALID;
+  if (n == 0) return GSB_OK;
+  if (!keys_in || !vals_in || !keys_out || !vals_out || !tmp) return GSB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nz = (size_t)n, kb = align_up(nz * key_bytes), vb = align_up(nz * 4);
+  char* base = static_cast<char*>(tmp);
+  void* kA = base; uint32_t* vA = reinterpret_cast<uint32_t*>(base + kb);
+  void* kB = base + kb + vb; uint32_t* vB = reinterpret_cast<uint32_t*>(base + 2 * kb + vb);
+  void* hist = base + 2 * (kb + vb);
+  const int passes = radix_num_passes(end_bit);
+  // make the final buffer the caller's output
+  if (radix_result_in_A(passes)) { kA = keys_out; vA = vals_out; } else { kB = keys_out; vB = vals_out; }
+  if (passes == 0) {
+    GSB_CUDA(cudaMemcpyAsync(keys_out, keys_in, nz * key_bytes, cudaMemcpyDeviceToDevice, st));
+    GSB_CUDA(cudaMemcpyAsync(vals_out, vals_in, nz * 4, cudaMemcpyDeviceToDevice, st));
+    return GSB_OK;
+  }
+  if (key_bytes == 4)
+    return radix_sort_pairs<uint32_t>(n, nullptr, (const uint32_t*)keys_in, vals_in, (uint32_t*)kA, vA,
+                                      (uint32_t*)kB, vB, end_bit, false, hist, false, st);
+  return radix_sort_pairs<uint64_t>(n, nullptr, (const uint64_t*)keys_in, vals_in, (uint64_t*)kA, vA,
+                                    (uint64_t*)kB, vB, end_bit, false, hist, false, st);
+}
+
+int gsb_radix_sort_pairs_u32(long long n, const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                             uint32_t* vals_out, int end_bit, void* tmp, void* stream) {
+  return radix_entry(n, keys_in, vals_in, keys_out, vals_out, end_bit, tmp, stream, 4);
+}
+
+int gsb_radix_sort_pairs_u64(long long n, const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out,
+                             uint32_t* vals_out, int end_bit, void* tmp, void* stream) {
+  return radix_entry(n, keys_in, vals_in, keys_out, vals_out, end_bit, tmp, stream, 8);
+}
+
+}  // extern "C"

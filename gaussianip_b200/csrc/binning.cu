@@ -1,0 +1,457 @@
+// Stage 2: binning.  Replaces InclusiveSum + duplicateWithKeys + cub::DeviceRadixSort +
+// identifyTileRanges of the external operator ("Binning") with
+// hand-written kernels: a stable LSD radix sort (8-bit digits; per-block histograms,
+// row scan, match-based stable in-block ranking), a gathered scan + instance emission, and a
+// tile-boundary pass.
+//
+// Two modes produce the IDENTICAL instance order (tile, then depth bits, then Gaussian id):
+//   GSB_BIN_TWO_LEVEL  sort the P Gaussians once by 32-bit depth key (4 passes over P), emit
+//                      instances in that order, then stably partition the D instances by tile
+//                      id (ceil(log2 T / 8) passes over D) — ~2.6x less traffic at D = 2P;
+//   GSB_BIN_FLAT64     emit (tile<<32|depth) keys in Gaussian order and sort all D 64-bit
+//                      keys (the reference's structure; kept for cross-checks).
+// Everything that depends on D reads it from device memory (counts[CNT_D]); grids are sized
+// by the capacity D_cap, so the host never synchronises to learn D.
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_IPT = 16;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per block
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ long long load_n(const uint32_t* d_n, long long n_cap) {
+  if (!d_n) return n_cap;
+  long long n = (long long)*d_n;
+  return n < n_cap ? n : n_cap;
+}
+
+template <typename KeyT>
+__device__ __forceinline__ uint32_t digit_of(KeyT k, int shift) {
+  return (uint32_t)(k >> shift) & 0xFFu;
+}
+
+// exclusive scan of one value per thread over a 256-thread block; returns exclusive prefix,
+// *total receives the block sum.  s_warp must hold 8 uint32.
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t wsum = (lane < RS_WARPS) ? s_warp[lane] : 0;
+#pragma unroll
+  for (int o = 1; o < RS_WARPS; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, wsum, o);
+    if (lane >= o) wsum += t;
+  }
+  const uint32_t wprefix = __shfl_sync(0xffffffffu, wsum, warp) - s_warp[warp];
+  if (total) *total = __shfl_sync(0xffffffffu, wsum, RS_WARPS - 1);
+  __syncthreads();
+  return wprefix + inc - v;
+}
+
+// ---- radix sort -----------------------------------------------------------------------------
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ d_n, long long n_cap, int shift,
+                  uint32_t* __restrict__ hist, int num_blocks) {
+  __shared__ uint32_t s_h[256];
+  const long long n = load_n(d_n, n_cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s_h[tid] = 0;
+  __syncthreads();
+  const long long seg = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_IPT * 32);
+  if ((long long)blockIdx.x * RS_TILE < n) {
+#pragma unroll 4
+    for (int r = 0; r < RS_IPT; ++r) {
+      const long long idx = seg + r * 32 + lane;
+      const bool valid = idx < n;
+      const uint32_t d = valid ? digit_of(keys[idx], shift) : 0x100u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_h[d], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  hist[(size_t)tid * num_blocks + blockIdx.x] = s_h[tid];
+}
+
+// one block per digit: in-place exclusive scan of that digit's row of per-block counts
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scan_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ totals, int num_blocks) {
+  __shared__ uint32_t s_warp[RS_WARPS];
+  uint32_t* row = hist + (size_t)blockIdx.x * num_blocks;
+  uint32_t carry = 0;
+  for (int base = 0; base < num_blocks; base += RS_THREADS) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < num_blocks ? row[i] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan_256(v, s_warp, &total);
+    if (i < num_blocks) row[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+template <typename KeyT, bool IOTA>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                     const uint32_t* __restrict__ d_n, long long n_cap, int shift,
+                     const uint32_t* __restrict__ hist, const uint32_t* __restrict__ totals, int num_blocks) {
+  __shared__ uint32_t s_cnt[RS_WARPS][256];
+  __shared__ uint32_t s_warp[RS_WARPS];
+  const long long n = load_n(d_n, n_cap);
+  const long long block_base = (long long)blockIdx.x * RS_TILE;
+  if (block_base >= n) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][tid] = 0;
+  const uint32_t dbase = block_exclusive_scan_256(totals[tid], s_warp, nullptr);  // syncs inside
+  const uint32_t gbase = dbase + hist[(size_t)tid * num_blocks + blockIdx.x];
+
+  KeyT key[RS_IPT];
+  uint32_t val[RS_IPT];
+  uint32_t rank[RS_IPT];
+  const long long seg = block_base + (long long)warp * (RS_IPT * 32);
+  const uint32_t lt = lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const long long idx = seg + r * 32 + lane;
+    const bool valid = idx < n;
+    key[r] = valid ? keys_in[idx] : (KeyT)0;
+    val[r] = valid ? (IOTA ? (uint32_t)idx : vals_in[idx]) : 0u;
+    const uint32_t d = valid ? digit_of(key[r], shift) : 0x100u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && lane == leader) {
+      old = s_cnt[warp][d];
+      s_cnt[warp][d] = old + (uint32_t)__popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + (uint32_t)__popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    uint32_t run = gbase;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = s_cnt[w][tid];
+      s_cnt[w][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const long long idx = seg + r * 32 + lane;
+    if (idx < n) {
+      const uint32_t pos = s_cnt[warp][digit_of(key[r], shift)] + rank[r];
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
+    }
+  }
+}
+
+// ---- scan of tiles_touched (gathered through an order) + instance emission -------------------
+
+constexpr int SC_IPT = 8;
+constexpr int SC_TILE = RS_THREADS * SC_IPT;  // 2048 Gaussians per block
+
+__global__ void __launch_bounds__(RS_THREADS)
+tiles_partial_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order, int P,
+                     uint32_t* __restrict__ blocksums) {
+  __shared__ uint32_t s_warp[RS_WARPS];
+  const int base = blockIdx.x * SC_TILE;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; ++k) {
+    const int j = base + k * RS_THREADS + threadIdx.x;
+    if (j < P) sum += tiles[order ? order[j] : j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < RS_WARPS; ++w) t += s_warp[w];
+    blocksums[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of the per-block sums; publishes D and the overflow flag
+__global__ void __launch_bounds__(RS_THREADS)
+scan_blocksums_kernel(uint32_t* __restrict__ blocksums, int num_blocks, uint32_t* __restrict__ counts,
+                      long long D_cap, int mode) {
+  __shared__ uint32_t s_warp[RS_WARPS];
+  unsigned long long carry = 0;
+  for (int base = 0; base < num_blocks; base += RS_THREADS) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < num_blocks ? blocksums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan_256(v, s_warp, &total);
+    if (i < num_blocks) blocksums[i] = (uint32_t)carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long D = carry;
+    counts[CNT_D] = D > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)D;
+    counts[CNT_OVERFLOW] = D > (unsigned long long)D_cap ? 1u : 0u;
+    counts[4] = (uint32_t)mode;
+  }
+}
+
+// MODE 0: write (tile id, Gaussian id) ; MODE 1: write (tile<<32|depth, Gaussian id)
+template <int MODE>
+__global__ void __launch_bounds__(RS_THREADS)
+emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order, int P,
+            const uint32_t* __restrict__ blocksums, const ushort4* __restrict__ rect,
+            const uint32_t* __restrict__ dkeys, int gx, long long D_cap, uint32_t* __restrict__ tkeys,
+            uint64_t* __restrict__ keys64, uint32_t* __restrict__ vals) {
+  __shared__ uint32_t s_warp[RS_WARPS];
+  // blocked arrangement: thread t owns SC_IPT consecutive Gaussians of the emission order
+  const int first = blockIdx.x * SC_TILE + threadIdx.x * SC_IPT;
+  uint32_t gid[SC_IPT], cnt[SC_IPT];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; ++k) {
+    const int j = first + k;
+    gid[k] = 0; cnt[k] = 0;
+    if (j < P) {
+      gid[k] = order ? order[j] : (uint32_t)j;
+      cnt[k] = tiles[gid[k]];
+    }
+    mine += cnt[k];
+  }
+  uint32_t off = blocksums[blockIdx.x] + block_exclusive_scan_256(mine, s_warp, nullptr);
+#pragma unroll
+  for (int k = 0; k < SC_IPT; ++k) {
+    if (cnt[k] == 0) continue;
+    const ushort4 rc = rect[gid[k]];
+    const uint32_t dk = (MODE == 1) ? dkeys[gid[k]] : 0u;
+    long long o = off;
+    for (int y = rc.y; y < rc.w; ++y) {
+      for (int x = rc.x; x < rc.z; ++x) {
+        if (o < D_cap) {
+          const uint32_t tile = (uint32_t)(y * gx + x);
+          if (MODE == 0) tkeys[o] = tile;
+          else keys64[o] = ((uint64_t)tile << 32) | dk;
+          vals[o] = gid[k];
+        }
+        ++o;
+      }
+    }
+    off += cnt[k];
+  }
+}
+
+template <typename KeyT>
+__global__ void tile_ranges_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ d_n,
+                                   long long n_cap, uint2* __restrict__ ranges) {
+  const long long n = load_n(d_n, n_cap);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int sh = sizeof(KeyT) == 8 ? 32 : 0;
+  const uint32_t t = (uint32_t)(keys[i] >> sh);
+  if (i == 0) ranges[t].x = 0;
+  else {
+    const uint32_t p = (uint32_t)(keys[i - 1] >> sh);
+    if (p != t) { ranges[p].y = (uint32_t)i; ranges[t].x = (uint32_t)i; }
+  }
+  if (i == n - 1) ranges[t].y = (uint32_t)n;
+}
+
+__global__ void compose_keys_kernel(const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ point_list,
+                                    const uint32_t* __restrict__ dkeys, const uint32_t* __restrict__ d_n,
+                                    long long n_cap, uint64_t* __restrict__ out) {
+  const long long n = load_n(d_n, n_cap);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = ((uint64_t)tkeys[i] << 32) | dkeys[point_list[i]];
+}
+
+inline int bits_for(unsigned int max_value) {  // bits needed to represent values in [0, max_value]
+  int b = 0;
+  while (max_value) { ++b; max_value >>= 1; }
+  return b;
+}
+
+}  // namespace
+
+int radix_num_passes(int end_bit) { return (end_bit + 7) / 8; }
+bool radix_result_in_A(int passes) { return (passes & 1) != 0; }
+
+size_t radix_tmp_bytes(long long n_cap) {
+  const long long nb = (n_cap + RS_TILE - 1) / RS_TILE;
+  return (size_t)(256 * (nb > 0 ? nb : 1) + 256) * sizeof(uint32_t);
+}
+
+// Stable LSD sort on bits [0,end_bit).  Pass 0 reads (src_keys, src_vals); pass p writes
+// buffer A when p is even and buffer B when p is odd.  src may alias B (never A).  The result
+// is in A when the number of passes is odd, in B when it is even (see radix_result_in_A).
+template <typename KeyT>
+int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys, const uint32_t* src_vals,
+                     KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
+                     bool iota_vals, void* tmp, bool debug, cudaStream_t st) {
+  if (n_cap <= 0) return GSB_OK;
+  const int nb = (int)((n_cap + RS_TILE - 1) / RS_TILE);
+  uint32_t* hist = static_cast<uint32_t*>(tmp);
+  uint32_t* totals = hist + (size_t)256 * nb;
+  const int passes = radix_num_passes(end_bit);
+  for (int p = 0; p < passes; ++p) {
+    const KeyT* kin = p == 0 ? src_keys : ((p & 1) ? keysA : keysB);
+    const uint32_t* vin = p == 0 ? src_vals : ((p & 1) ? valsA : valsB);
+    KeyT* kout = (p & 1) ? keysB : keysA;
+    uint32_t* vout = (p & 1) ? valsB : valsA;
+    const int shift = 8 * p;
+    radix_hist_kernel<KeyT><<<nb, RS_THREADS, 0, st>>>(kin, d_n, n_cap, shift, hist, nb);
+    GSB_POST_LAUNCH(debug, st, "radix_hist_kernel");
+    radix_scan_kernel<<<256, RS_THREADS, 0, st>>>(hist, totals, nb);
+    GSB_POST_LAUNCH(debug, st, "radix_scan_kernel");
+    if (p == 0 && iota_vals)
+      radix_scatter_kernel<KeyT, true><<<nb, RS_THREADS, 0, st>>>(kin, vin, kout, vout, d_n, n_cap, shift,
+                                                                  hist, totals, nb);
+    else
+      radix_scatter_kernel<KeyT, false><<<nb, RS_THREADS, 0, st>>>(kin, vin, kout, vout, d_n, n_cap, shift,
+                                                                   hist, totals, nb);
+    GSB_POST_LAUNCH(debug, st, "radix_scatter_kernel");
+  }
+  return GSB_OK;
+}
+
+template int radix_sort_pairs<uint32_t>(long long, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*,
+                                        uint32_t*, uint32_t*, uint32_t*, int, bool, void*, bool, cudaStream_t);
+template int radix_sort_pairs<uint64_t>(long long, const uint32_t*, const uint64_t*, const uint32_t*, uint64_t*,
+                                        uint32_t*, uint64_t*, uint32_t*, int, bool, void*, bool, cudaStream_t);
+
+int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbLayout& L,
+                    long long D_cap, int mode, uint32_t* host_counts, cudaEvent_t event, bool debug,
+                    cudaStream_t st) {
+  uint32_t* counts = at<uint32_t>(saved, L.off_counts);
+  uint32_t* point_list = at<uint32_t>(saved, L.off_point_list);
+  uint2* ranges = at<uint2>(saved, L.off_ranges);
+  const ushort4* rect = at<ushort4>(scratch, L.off_rect);
+  const uint32_t* tiles = at<uint32_t>(scratch, L.off_tiles);
+  const uint32_t* dkeys = at<uint32_t>(scratch, L.off_dkeys0);   // written by preprocess, kept intact
+  uint32_t* blocksums = at<uint32_t>(scratch, L.off_blocksums);
+  void* hist = at<char>(scratch, L.off_hist);
+  const int T = v.gx * v.gy;
+  GSB_CUDA(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), st));
+  auto publish = [&]() -> int {
+    if (host_counts)
+      GSB_CUDA(cudaMemcpyAsync(host_counts, counts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (event) GSB_CUDA(cudaEventRecord(event, st));
+    return GSB_OK;
+  };
+  if (P == 0) {
+    GSB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(uint32_t), st));
+    return publish();
+  }
+  const int sc_blocks = (P + SC_TILE - 1) / SC_TILE;
+  const int tile_bits = bits_for((unsigned)(T - 1));
+  const int cap_blocks = (int)((D_cap + 255) / 256);
+  uint32_t* alt_vals = at<uint32_t>(scratch, L.off_tvals_alt);
+  int rc;
+
+  if (mode == GSB_BIN_TWO_LEVEL) {
+    // (1) Gaussians by depth key (ties by index: the sort is stable and values start as iota)
+    uint32_t* kA = at<uint32_t>(scratch, L.off_dkeys1);
+    uint32_t* vA = at<uint32_t>(scratch, L.off_didx0);
+    uint32_t* kB = at<uint32_t>(scratch, L.off_dkeys2);
+    uint32_t* vB = at<uint32_t>(scratch, L.off_didx1);
+    rc = radix_sort_pairs<uint32_t>(P, nullptr, dkeys, nullptr, kA, vA, kB, vB, 32, true, hist, debug, st);
+    if (rc) return rc;
+    const uint32_t* order = vB;  // 4 passes -> result in B
+    // (2) offsets in that order, D, overflow flag
+    tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums);
+    GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
+    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode);
+    GSB_POST_LAUNCH(debug, st, "scan_blocksums_kernel");
+    if ((rc = publish())) return rc;
+    // (3) emit (tile id, Gaussian id) in (depth, id, tile) order, then stable partition by tile
+    const bool inA = radix_result_in_A(radix_num_passes(tile_bits));
+    uint32_t* tkA = at<uint32_t>(scratch, L.off_tkeys0);
+    uint32_t* tkB = at<uint32_t>(scratch, L.off_tkeys1);
+    uint32_t* tvA = inA ? point_list : alt_vals;
+    uint32_t* tvB = inA ? alt_vals : point_list;
+    emit_kernel<0><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums, rect, dkeys, v.gx, D_cap, tkB,
+                                                     nullptr, tvB);
+    GSB_POST_LAUNCH(debug, st, "emit_kernel");
+    rc = radix_sort_pairs<uint32_t>(D_cap, counts + CNT_D, tkB, tvB, tkA, tvA, tkB, tvB, tile_bits, false, hist,
+                                    debug, st);
+    if (rc) return rc;
+    // (a single-tile image needs 0 passes: the emitted order in B is already final)
+    tile_ranges_kernel<uint32_t><<<cap_blocks, 256, 0, st>>>(inA ? tkA : tkB, counts + CNT_D, D_cap, ranges);
+    GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
+    return GSB_OK;
+  }
+  if (mode == GSB_BIN_FLAT64) {
+    tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums);
+    GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
+    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode);
+    GSB_POST_LAUNCH(debug, st, "scan_blocksums_kernel");
+    if ((rc = publish())) return rc;
+    const int end_bit = 32 + tile_bits;
+    const bool inA = radix_result_in_A(radix_num_passes(end_bit));
+    uint64_t* kA = at<uint64_t>(scratch, L.off_keys64_0);
+    uint64_t* kB = at<uint64_t>(scratch, L.off_keys64_1);
+    uint32_t* tvA = inA ? point_list : alt_vals;
+    uint32_t* tvB = inA ? alt_vals : point_list;
+    emit_kernel<1><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums, rect, dkeys, v.gx, D_cap,
+                                                     nullptr, kB, tvB);
+    GSB_POST_LAUNCH(debug, st, "emit_kernel");
+    rc = radix_sort_pairs<uint64_t>(D_cap, counts + CNT_D, kB, tvB, kA, tvA, kB, tvB, end_bit, false, hist, debug,
+                                    st);
+    if (rc) return rc;
+    tile_ranges_kernel<uint64_t><<<cap_blocks, 256, 0, st>>>(inA ? kA : kB, counts + CNT_D, D_cap, ranges);
+    GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
+    return GSB_OK;
+  }
+  return GSB_E_INVALID;
+}
+
+int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void* scratch, const GsbLayout& L,
+                             long long D_cap, uint64_t* keys_out, cudaStream_t st) {
+  (void)P;
+  const uint32_t* counts = at<uint32_t>(saved, L.off_counts);
+  uint32_t h_counts[8];
+  GSB_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+  GSB_CUDA(cudaStreamSynchronize(st));
+  const int mode = (int)h_counts[4];
+  const long long n = h_counts[CNT_D] < (unsigned long long)D_cap ? h_counts[CNT_D] : D_cap;
+  if (n == 0) return GSB_OK;
+  const int T = v.gx * v.gy;
+  const int tile_bits = bits_for((unsigned)(T - 1));
+  if (mode == GSB_BIN_FLAT64) {
+    const bool inA = radix_result_in_A(radix_num_passes(32 + tile_bits));
+    const uint64_t* src = at<uint64_t>(scratch, inA ? L.off_keys64_0 : L.off_keys64_1);
+    GSB_CUDA(cudaMemcpyAsync(keys_out, src, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    return GSB_OK;
+  }
+  const bool inA = radix_result_in_A(radix_num_passes(tile_bits));
+  const uint32_t* tk = at<uint32_t>(scratch, inA ? L.off_tkeys0 : L.off_tkeys1);
+  compose_keys_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(tk, at<uint32_t>(saved, L.off_point_list),
+                                                              at<uint32_t>(scratch, L.off_dkeys0), counts + CNT_D,
+                                                              D_cap, keys_out);
+  GSB_POST_LAUNCH(false, st, "compose_keys_kernel");
+  return GSB_OK;
+}
+
+}  // namespace gsb

@@ -1,0 +1,120 @@
+// Internal declarations shared by the sm_100a kernels behind include/gsb.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gsb.h"
+
+namespace gsb {
+
+constexpr int TILE_X = 16;
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr float NEAR_Z = 0.2f;
+constexpr float LOWPASS = 0.3f;
+constexpr float ALPHA_CAP = 0.99f;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float T_MIN = 0.0001f;
+
+// Per-Gaussian record gathered by the blend kernels: 48 B, 16 B aligned, three float4.
+struct __align__(16) Geom {
+  float x, y, ca, cb;         // pixel centre, conic A, conic B
+  float cc, opacity, depth, r;  // conic C, opacity, view z, red
+  float g, b, extx, exty;     // green, blue, conservative half-extent of {alpha >= 1/255} in px
+};
+static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
+
+// Per-Gaussian gradient record accumulated by render_bwd (atomics land in one 48 B span).
+struct __align__(16) GGrad {
+  float dx, dy, dA, dB;       // dL/d(ndc xy), dL/dconic A, B
+  float dC, dop, ddepth, dr;  // dL/dconic C, dL/dopacity, dL/ddepth, dL/dred
+  float dg, db, pad0, pad1;
+};
+static_assert(sizeof(GGrad) == 48, "GGrad must be 48 bytes");
+
+enum Counts { CNT_D = 0, CNT_OVERFLOW = 1, CNT_VISIBLE = 2, CNT_MAXTILES = 3 };
+
+struct View {           // settings with device pointers, passed by value to kernels
+  int H, W, gx, gy;     // image size, tile grid
+  float tanfovx, tanfovy, focal_x, focal_y, scale_mod;
+  int sh_degree;
+  const float* bg;
+  const float* view;
+  const float* proj;
+  const float* campos;
+};
+
+inline View make_view(const GsbSettings* s) {
+  View v;
+  v.H = s->image_height; v.W = s->image_width;
+  v.gx = (v.W + TILE_X - 1) / TILE_X; v.gy = (v.H + TILE_Y - 1) / TILE_Y;
+  v.tanfovx = s->tanfovx; v.tanfovy = s->tanfovy;
+  v.focal_x = (float)v.W / (2.0f * s->tanfovx);
+  v.focal_y = (float)v.H / (2.0f * s->tanfovy);
+  v.scale_mod = s->scale_modifier; v.sh_degree = s->sh_degree;
+  v.bg = s->bg; v.view = s->viewmatrix; v.proj = s->projmatrix; v.campos = s->campos;
+  return v;
+}
+
+template <typename T>
+inline T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(base) + off); }
+template <typename T>
+inline const T* at(const void* base, size_t off) {
+  return reinterpret_cast<const T*>(static_cast<const char*>(base) + off);
+}
+
+// error plumbing (api.cu)
+int cuda_fail(cudaError_t e, const char* what);
+#define GSB_CUDA(call)                                          \
+  do {                                                          \
+    cudaError_t e__ = (call);                                   \
+    if (e__ != cudaSuccess) return gsb::cuda_fail(e__, #call);  \
+  } while (0)
+// after a kernel launch: always catch launch errors; in debug mode also synchronise
+#define GSB_POST_LAUNCH(dbg, st, name)                                              \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ == cudaSuccess && (dbg)) e__ = cudaStreamSynchronize(st);               \
+    if (e__ != cudaSuccess) return gsb::cuda_fail(e__, name);                       \
+  } while (0)
+
+// ---- stage launchers (one per .cu) -------------------------------------------------------
+int launch_preprocess_fwd(const View& v, int P, int K, const float* means3D, const float* scales,
+                          const float* rots, const float* opac, const float* shs,
+                          const float* colors, const float* cov3D, int32_t* radii, Geom* geom,
+                          uint8_t* clamped, ushort4* rect, uint32_t* tiles, uint32_t* dkeys,
+                          uint32_t* counts, bool debug, cudaStream_t st);
+
+int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbLayout& L,
+                    long long D_cap, int mode, uint32_t* host_counts, cudaEvent_t event, bool debug,
+                    cudaStream_t st);
+
+int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
+                      const uint2* ranges, float* color, float* depth, float* alpha,
+                      uint32_t* n_contrib, float* final_T, bool debug, cudaStream_t st);
+
+int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
+                      const uint2* ranges, const uint32_t* n_contrib, const float* final_T,
+                      const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                      GGrad* ggrad, bool debug, cudaStream_t st);
+
+int launch_preprocess_bwd(const View& v, int P, int K, const float* means3D, const float* scales,
+                          const float* rots, const float* opac, const float* shs,
+                          const float* colors, const float* cov3D, const int32_t* radii,
+                          const Geom* geom, const uint8_t* clamped, const GGrad* ggrad,
+                          float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors,
+                          float* dopac, float* dscales, float* drots, float* dcov3D,
+                          int accumulate, bool debug, cudaStream_t st);
+
+// radix sort (binning.cu)
+size_t radix_tmp_bytes(long long n_cap);
+template <typename KeyT>
+int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys, const uint32_t* src_vals,
+                     KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
+                     bool iota_vals, void* tmp, bool debug, cudaStream_t st);
+bool radix_result_in_A(int passes);
+int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void* scratch, const GsbLayout& L,
+                             long long D_cap, uint64_t* keys_out, cudaStream_t st);
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
+int radix_num_passes(int end_bit);
+
+}  // namespace gsb

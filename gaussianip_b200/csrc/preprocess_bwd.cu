@@ -1,0 +1,292 @@
+// Backward stage 2: per-Gaussian gradients.  Replaces computeCov2DCUDA + preprocessCUDA
+// (backward) of the external operator ("Backward preprocess") in one
+// kernel: conic -> cov2D -> (cov3D, view-space mean) -> (scale, rotation, mean), plus the
+// mean gradient through the perspective divide (means2D), the depth output and the SH
+// colour.  One thread per Gaussian; the forward intermediates are recomputed from the
+// inputs instead of being stored (saves 24 B/Gaussian of cov3D traffic each way).
+// With accumulate != 0 results are added to the outputs (beta = 1) so all views of a step
+// land in one gradient bucket.
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+namespace {
+
+__device__ __forceinline__ void put(float* p, float v, int acc) { *p = acc ? (*p + v) : v; }
+
+__global__ void __launch_bounds__(256)
+preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
+                      const float* __restrict__ scales, const float* __restrict__ rots,
+                      const float* __restrict__ shs, const float* __restrict__ cov3Dp,
+                      const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
+                      const GGrad* __restrict__ ggrad, float* __restrict__ dmeans3D,
+                      float* __restrict__ dmeans2D, float* __restrict__ dshs, float* __restrict__ dcolors,
+                      float* __restrict__ dopac, float* __restrict__ dscales, float* __restrict__ drots,
+                      float* __restrict__ dcov3D, int acc) {
+  __shared__ float sV[16], sM[16], sCam[3];
+  if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sM[threadIdx.x] = v.proj[threadIdx.x]; }
+  if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int ncoef = (v.sh_degree + 1) * (v.sh_degree + 1);
+
+  if (radii[i] <= 0) {
+    if (!acc) {  // gradients of culled Gaussians are exactly 0
+      dmeans3D[3 * i] = dmeans3D[3 * i + 1] = dmeans3D[3 * i + 2] = 0.f;
+      dmeans2D[3 * i] = dmeans2D[3 * i + 1] = dmeans2D[3 * i + 2] = 0.f;
+      dopac[i] = 0.f;
+      if (dshs) for (int k = 0; k < 3 * K; ++k) dshs[(size_t)i * K * 3 + k] = 0.f;
+      if (dcolors) dcolors[3 * i] = dcolors[3 * i + 1] = dcolors[3 * i + 2] = 0.f;
+      if (dscales) dscales[3 * i] = dscales[3 * i + 1] = dscales[3 * i + 2] = 0.f;
+      if (drots) reinterpret_cast<float4*>(drots)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dcov3D) for (int k = 0; k < 6; ++k) dcov3D[6 * (size_t)i + k] = 0.f;
+    }
+    return;
+  }
+
+  const float4* gp = reinterpret_cast<const float4*>(ggrad + i);
+  const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+  const float gx = g0.x, gy = g0.y, gA = g0.z, gB = g0.w, gC = g1.x, gop = g1.y, gdepth = g1.z;
+  float grgb[3] = {g1.w, g2.x, g2.y};
+
+  const float px = means3D[3 * i], py = means3D[3 * i + 1], pz = means3D[3 * i + 2];
+  const float tx = sV[0] * px + sV[4] * py + sV[8] * pz + sV[12];
+  const float ty = sV[1] * px + sV[5] * py + sV[9] * pz + sV[13];
+  const float tz = sV[2] * px + sV[6] * py + sV[10] * pz + sV[14];
+  float dpx = 0.f, dpy = 0.f, dpz = 0.f;
+
+  // ---- colour -------------------------------------------------------------------------
+  if (dcolors) {
+    put(dcolors + 3 * i, grgb[0], acc); put(dcolors + 3 * i + 1, grgb[1], acc); put(dcolors + 3 * i + 2, grgb[2], acc);
+  } else {
+    const uint8_t cl = clamped[i];
+    if (cl & 1) grgb[0] = 0.f;
+    if (cl & 2) grgb[1] = 0.f;
+    if (cl & 4) grgb[2] = 0.f;
+    const float ox = px - sCam[0], oy = py - sCam[1], oz = pz - sCam[2];
+    const float sum2 = ox * ox + oy * oy + oz * oz;
+    const float inv = rsqrtf(sum2);
+    const float x = ox * inv, y = oy * inv, z = oz * inv;
+    const float* sh = shs + (size_t)i * K * 3;
+    float* dsh = dshs + (size_t)i * K * 3;
+    const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
+    float basis[16];
+    float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
+    basis[0] = C0;
+    if (v.sh_degree > 0) {
+      basis[1] = -C1 * y; basis[2] = C1 * z; basis[3] = -C1 * x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ddx[c] = -C1 * sh[9 + c]; ddy[c] = -C1 * sh[3 + c]; ddz[c] = C1 * sh[6 + c];
+      }
+      if (v.sh_degree > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        const float a0 = 1.0925484305920792f, a1 = -1.0925484305920792f, a2 = 0.31539156525252005f,
+                    a3 = -1.0925484305920792f, a4 = 0.5462742152960396f;
+        basis[4] = a0 * xy; basis[5] = a1 * yz; basis[6] = a2 * (2.f * zz - xx - yy);
+        basis[7] = a3 * xz; basis[8] = a4 * (xx - yy);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          ddx[c] += a0 * y * sh[12 + c] + a2 * (-2.f * x) * sh[18 + c] + a3 * z * sh[21 + c] + a4 * 2.f * x * sh[24 + c];
+          ddy[c] += a0 * x * sh[12 + c] + a1 * z * sh[15 + c] + a2 * (-2.f * y) * sh[18 + c] + a4 * (-2.f * y) * sh[24 + c];
+          ddz[c] += a1 * y * sh[15 + c] + a2 * 4.f * z * sh[18 + c] + a3 * x * sh[21 + c];
+        }
+        if (v.sh_degree > 2) {
+          const float b0 = -0.5900435899266435f, b1 = 2.890611442640554f, b2 = -0.4570457994644658f,
+                      b3 = 0.3731763325901154f, b4 = -0.4570457994644658f, b5 = 1.445305721320277f,
+                      b6 = -0.5900435899266435f;
+          basis[9] = b0 * y * (3.f * xx - yy);
+          basis[10] = b1 * xy * z;
+          basis[11] = b2 * y * (4.f * zz - xx - yy);
+          basis[12] = b3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+          basis[13] = b4 * x * (4.f * zz - xx - yy);
+          basis[14] = b5 * z * (xx - yy);
+          basis[15] = b6 * x * (xx - 3.f * yy);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            ddx[c] += b0 * sh[27 + c] * 6.f * xy + b1 * sh[30 + c] * yz + b2 * sh[33 + c] * (-2.f * xy) +
+                      b3 * sh[36 + c] * (-6.f * xz) + b4 * sh[39 + c] * (4.f * zz - 3.f * xx - yy) +
+                      b5 * sh[42 + c] * 2.f * xz + b6 * sh[45 + c] * (3.f * xx - 3.f * yy);
+            ddy[c] += b0 * sh[27 + c] * (3.f * xx - 3.f * yy) + b1 * sh[30 + c] * xz +
+                      b2 * sh[33 + c] * (4.f * zz - xx - 3.f * yy) + b3 * sh[36 + c] * (-6.f * yz) +
+                      b4 * sh[39 + c] * (-2.f * xy) + b5 * sh[42 + c] * (-2.f * yz) + b6 * sh[45 + c] * (-6.f * xy);
+            ddz[c] += b1 * sh[30 + c] * xy + b2 * sh[33 + c] * 8.f * yz + b3 * sh[36 + c] * (6.f * zz - 3.f * xx - 3.f * yy) +
+                      b4 * sh[39 + c] * 8.f * xz + b5 * sh[42 + c] * (xx - yy);
+          }
+        }
+      }
+    }
+    for (int k = 0; k < K; ++k) {
+      const float bk = k < ncoef ? basis[k] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (k < ncoef) put(dsh + 3 * k + c, bk * grgb[c], acc);
+        else if (!acc) dsh[3 * k + c] = 0.f;
+      }
+    }
+    // through the view direction normalisation
+    const float dLx = ddx[0] * grgb[0] + ddx[1] * grgb[1] + ddx[2] * grgb[2];
+    const float dLy = ddy[0] * grgb[0] + ddy[1] * grgb[1] + ddy[2] * grgb[2];
+    const float dLz = ddz[0] * grgb[0] + ddz[1] * grgb[1] + ddz[2] * grgb[2];
+    const float inv3 = inv * inv * inv;
+    dpx += ((sum2 - ox * ox) * dLx - oy * ox * dLy - oz * ox * dLz) * inv3;
+    dpy += (-ox * oy * dLx + (sum2 - oy * oy) * dLy - oz * oy * dLz) * inv3;
+    dpz += (-ox * oz * dLx - oy * oz * dLy + (sum2 - oz * oz) * dLz) * inv3;
+  }
+
+  // ---- 3D covariance (recomputed) -------------------------------------------------------
+  float S00, S01, S02, S11, S12, S22;
+  float m[3][3], R[3][3], s[3] = {0.f, 0.f, 0.f};
+  float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+  if (cov3Dp) {
+    const float* c = cov3Dp + 6 * (size_t)i;
+    S00 = c[0]; S01 = c[1]; S02 = c[2]; S11 = c[3]; S12 = c[4]; S22 = c[5];
+  } else {
+    s[0] = v.scale_mod * scales[3 * i]; s[1] = v.scale_mod * scales[3 * i + 1]; s[2] = v.scale_mod * scales[3 * i + 2];
+    const float4 q = reinterpret_cast<const float4*>(rots)[i];
+    qr = q.x; qx = q.y; qy = q.z; qz = q.w;
+    R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
+    R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
+    R[2][0] = 2.f * (qx * qz - qr * qy); R[2][1] = 2.f * (qy * qz + qr * qx); R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) m[a][k] = R[a][k] * s[k];
+    S00 = m[0][0] * m[0][0] + m[0][1] * m[0][1] + m[0][2] * m[0][2];
+    S01 = m[0][0] * m[1][0] + m[0][1] * m[1][1] + m[0][2] * m[1][2];
+    S02 = m[0][0] * m[2][0] + m[0][1] * m[2][1] + m[0][2] * m[2][2];
+    S11 = m[1][0] * m[1][0] + m[1][1] * m[1][1] + m[1][2] * m[1][2];
+    S12 = m[1][0] * m[2][0] + m[1][1] * m[2][1] + m[1][2] * m[2][2];
+    S22 = m[2][0] * m[2][0] + m[2][1] * m[2][1] + m[2][2] * m[2][2];
+  }
+
+  // ---- EWA projection (recomputed) and its backward ------------------------------------------
+  const float limx = 1.3f * v.tanfovx, limy = 1.3f * v.tanfovy;
+  const float tz_inv = 1.0f / tz;
+  const float txtz = tx * tz_inv, tytz = ty * tz_inv;
+  const float x_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+  const float y_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+  const float txc = fminf(limx, fmaxf(-limx, txtz)) * tz;
+  const float tyc = fminf(limy, fmaxf(-limy, tytz)) * tz;
+  const float tz2 = tz_inv * tz_inv, tz3 = tz2 * tz_inv;
+  const float fx = v.focal_x, fy = v.focal_y;
+  const float J00 = fx * tz_inv, J02 = -fx * txc * tz2, J11 = fy * tz_inv, J12 = -fy * tyc * tz2;
+  float T0[3], T1[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    T0[j] = J00 * sV[0 + 4 * j] + J02 * sV[2 + 4 * j];
+    T1[j] = J11 * sV[1 + 4 * j] + J12 * sV[2 + 4 * j];
+  }
+  const float Sg[3][3] = {{S00, S01, S02}, {S01, S11, S12}, {S02, S12, S22}};
+  float U0[3], U1[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    U0[j] = T0[0] * Sg[0][j] + T0[1] * Sg[1][j] + T0[2] * Sg[2][j];
+    U1[j] = T1[0] * Sg[0][j] + T1[1] * Sg[1][j] + T1[2] * Sg[2][j];
+  }
+  const float a = U0[0] * T0[0] + U0[1] * T0[1] + U0[2] * T0[2] + LOWPASS;
+  const float b = U0[0] * T1[0] + U0[1] * T1[1] + U0[2] * T1[2];
+  const float c = U1[0] * T1[0] + U1[1] * T1[1] + U1[2] * T1[2] + LOWPASS;
+  const float det = a * c - b * b;
+  const float d2 = 1.0f / (det * det + 0.0000001f);
+  float ga = 0.f, gb = 0.f, gc = 0.f;
+  if (det != 0.0f) {
+    ga = d2 * (-c * c * gA + b * c * gB + (det - a * c) * gC);
+    gc = d2 * (-a * a * gC + a * b * gB + (det - a * c) * gA);
+    gb = d2 * (2.f * b * c * gA - (det + 2.f * b * b) * gB + 2.f * a * b * gC);
+  }
+  // dL/dSigma (all nine entries independent): Gs = T^T [[ga, gb/2],[gb/2, gc]] T
+  float Gs[3][3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      Gs[p][q] = T0[p] * T0[q] * ga + 0.5f * (T0[p] * T1[q] + T1[p] * T0[q]) * gb + T1[p] * T1[q] * gc;
+
+  float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float dT0 = 2.f * ga * U0[j] + gb * U1[j];
+    const float dT1 = gb * U0[j] + 2.f * gc * U1[j];
+    dJ00 += dT0 * sV[0 + 4 * j]; dJ02 += dT0 * sV[2 + 4 * j];
+    dJ11 += dT1 * sV[1 + 4 * j]; dJ12 += dT1 * sV[2 + 4 * j];
+  }
+  const float dtx = x_mul * (-fx * tz2 * dJ02);
+  const float dty = y_mul * (-fy * tz2 * dJ12);
+  const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + 2.f * fx * txc * tz3 * dJ02 + 2.f * fy * tyc * tz3 * dJ12;
+  dpx += sV[0] * dtx + sV[1] * dty + sV[2] * dtz;
+  dpy += sV[4] * dtx + sV[5] * dty + sV[6] * dtz;
+  dpz += sV[8] * dtx + sV[9] * dty + sV[10] * dtz;
+
+  // ---- means2D (perspective divide) and depth -------------------------------------------
+  const float hx = sM[0] * px + sM[4] * py + sM[8] * pz + sM[12];
+  const float hy = sM[1] * px + sM[5] * py + sM[9] * pz + sM[13];
+  const float hw = sM[3] * px + sM[7] * py + sM[11] * pz + sM[15];
+  const float pw = 1.0f / (hw + 0.0000001f);
+  const float mul1 = hx * pw * pw, mul2 = hy * pw * pw;
+  dpx += (sM[0] * pw - sM[3] * mul1) * gx + (sM[1] * pw - sM[3] * mul2) * gy + sV[2] * gdepth;
+  dpy += (sM[4] * pw - sM[7] * mul1) * gx + (sM[5] * pw - sM[7] * mul2) * gy + sV[6] * gdepth;
+  dpz += (sM[8] * pw - sM[11] * mul1) * gx + (sM[9] * pw - sM[11] * mul2) * gy + sV[10] * gdepth;
+
+  put(dmeans3D + 3 * i, dpx, acc); put(dmeans3D + 3 * i + 1, dpy, acc); put(dmeans3D + 3 * i + 2, dpz, acc);
+  put(dmeans2D + 3 * i, gx, acc); put(dmeans2D + 3 * i + 1, gy, acc);
+  if (!acc) dmeans2D[3 * i + 2] = 0.f;
+  put(dopac + i, gop, acc);
+
+  // ---- cov3D -> scale / rotation ---------------------------------------------------------
+  if (cov3Dp) {
+    float* o = dcov3D + 6 * (size_t)i;
+    put(o + 0, Gs[0][0], acc); put(o + 1, 2.f * Gs[0][1], acc); put(o + 2, 2.f * Gs[0][2], acc);
+    put(o + 3, Gs[1][1], acc); put(o + 4, 2.f * Gs[1][2], acc); put(o + 5, Gs[2][2], acc);
+  } else {
+    float dM[3][3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        dM[p][k] = 2.f * (Gs[p][0] * m[0][k] + Gs[p][1] * m[1][k] + Gs[p][2] * m[2][k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      put(dscales + 3 * i + k, v.scale_mod * (R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k]), acc);
+    float dR[3][3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dR[p][k] = s[k] * dM[p][k];
+    const float dqr = 2.f * (-qz * dR[0][1] + qy * dR[0][2] + qz * dR[1][0] - qx * dR[1][2] - qy * dR[2][0] + qx * dR[2][1]);
+    const float dqx = 2.f * (qy * dR[0][1] + qz * dR[0][2] + qy * dR[1][0] - 2.f * qx * dR[1][1] - qr * dR[1][2] +
+                             qz * dR[2][0] + qr * dR[2][1] - 2.f * qx * dR[2][2]);
+    const float dqy = 2.f * (-2.f * qy * dR[0][0] + qx * dR[0][1] + qr * dR[0][2] + qx * dR[1][0] + qz * dR[1][2] -
+                             qr * dR[2][0] + qz * dR[2][1] - 2.f * qy * dR[2][2]);
+    const float dqz = 2.f * (-2.f * qz * dR[0][0] - qr * dR[0][1] + qx * dR[0][2] + qr * dR[1][0] - 2.f * qz * dR[1][1] +
+                             qy * dR[1][2] + qx * dR[2][0] + qy * dR[2][1]);
+    float4* o = reinterpret_cast<float4*>(drots) + i;
+    if (acc) {
+      const float4 old = *o;
+      *o = make_float4(old.x + dqr, old.y + dqx, old.z + dqy, old.w + dqz);
+    } else {
+      *o = make_float4(dqr, dqx, dqy, dqz);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_preprocess_bwd(const View& v, int P, int K, const float* means3D, const float* scales,
+                          const float* rots, const float* opac, const float* shs,
+                          const float* colors, const float* cov3D, const int32_t* radii,
+                          const Geom* geom, const uint8_t* clamped, const GGrad* ggrad,
+                          float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors,
+                          float* dopac, float* dscales, float* drots, float* dcov3D,
+                          int accumulate, bool debug, cudaStream_t st) {
+  (void)opac; (void)geom; (void)colors;
+  if (P == 0) return GSB_OK;
+  preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(v, P, K, means3D, scales, rots, shs, cov3D, radii,
+                                                         clamped, ggrad, dmeans3D, dmeans2D, dshs, dcolors,
+                                                         dopac, dscales, drots, dcov3D, accumulate);
+  GSB_POST_LAUNCH(debug, st, "preprocess_bwd_kernel");
+  return GSB_OK;
+}
+
+}  // namespace gsb

@@ -1,0 +1,348 @@
+"""Drop-in for the ``diff_gaussian_rasterization`` Python surface GaussianIP uses.
+
+Same names, argument meaning, return tuple and error behaviour as the operator the
+reference constructs at gaussiansplatting/gaussian_renderer/__init__.py:36-51 and calls at
+:85-93 (also :124-139/175-183, :213-228/240-248 and gs_renderer.py:943-958/992-1001):
+
+    settings   = GaussianRasterizationSettings(image_height=..., ..., debug=False)
+    rasterizer = GaussianRasterizer(raster_settings=settings)
+    color, radii, depth, alpha = rasterizer(means3D=..., means2D=..., shs=..., colors_precomp=...,
+                                            opacities=..., scales=..., rotations=..., cov3D_precomp=...)
+
+Host code is Python/PyTorch (device memory, streams, autograd plumbing); all arithmetic
+runs in the hand-written sm_100a kernels of libgsb.so through the C ABI in include/gsb.h.
+There is no CPU path: a missing library or a non-CUDA tensor raises.
+
+Differences from the external operator, by design (B200-first):
+* No device->host synchronisation to learn ``num_rendered``: instance buffers are sized by a
+  capacity that follows the scene, D is read back asynchronously right after the scan, and
+  the host only waits on that tiny copy (normally long finished).  If D exceeded the
+  capacity the forward is re-enqueued with a larger workspace before anything else can
+  observe the outputs.
+* The library never allocates: this module owns a per-(device, stream) scratch block and a
+  per-call ``saved`` block kept for backward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# ---- workspace --------------------------------------------------------------------------------
+
+class _Workspace:
+    """Transient scratch shared by all calls on one (device, stream)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.scratch: Optional[torch.Tensor] = None
+        self.d_cap = 0
+        self.host_counts = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(device))   # materialise the CUDA handle
+        self.binning_mode = _lib.BIN_TWO_LEVEL
+        self.last_num_rendered = 0
+        self.retries = 0
+
+    def capacity_for(self, P: int) -> int:
+        if self.d_cap == 0:
+            self.d_cap = max(1 << 16, 4 * P)
+        return self.d_cap
+
+    def ensure_scratch(self, nbytes: int) -> torch.Tensor:
+        if self.scratch is None or self.scratch.numel() < nbytes:
+            self.scratch = None
+            self.scratch = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=self.device)
+        return self.scratch
+
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device) -> _Workspace:
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = _Workspace(device)
+    return ws
+
+
+def set_binning_mode(mode: str, device=None) -> None:
+    """'two_level' (default) or 'flat64' (reference-structure 64-bit key sort); identical results."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _workspace(dev).binning_mode = {"two_level": _lib.BIN_TWO_LEVEL, "flat64": _lib.BIN_FLAT64}[mode]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check(t: torch.Tensor, name: str, shape_tail, device) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.device != device:
+        raise ValueError(f"{name} must be on {device}, got {t.device}")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != len(shape_tail) + 1 or tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"{name} must have shape [P, {', '.join(map(str, shape_tail))}], got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _small(t: torch.Tensor, n: int, name: str, device) -> torch.Tensor:
+    if not torch.is_tensor(t) or t.numel() != n:
+        raise ValueError(f"{name} must be a tensor with {n} elements")
+    if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+def _make_settings(rs: GaussianRasterizationSettings, device):
+    bg = _small(rs.bg, 3, "bg", device)
+    view = _small(rs.viewmatrix, 16, "viewmatrix", device)
+    proj = _small(rs.projmatrix, 16, "projmatrix", device)
+    campos = _small(rs.campos, 3, "campos", device)
+    if not (0 <= int(rs.sh_degree) <= 3):
+        raise ValueError("sh_degree must be in 0..3")
+    s = _lib.GsbSettings(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+                         float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)),
+                         int(bool(rs.debug)), bg.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                         campos.data_ptr())
+    return s, (bg, view, proj, campos)      # keep the tensors alive next to the struct
+
+
+class _Saved:
+    """Per-call state kept for backward (and exposed to the parity tests)."""
+    __slots__ = ("block", "layout", "d_cap", "P", "K", "H", "W", "num_rendered", "scratch", "settings_keep")
+
+    def view(self, off: int, nbytes: int, dtype) -> torch.Tensor:
+        return self.block[off:off + nbytes].view(dtype)
+
+    # named views -------------------------------------------------------------------------
+    def geom(self):
+        return self.view(self.layout.off_geom, self.P * 48, torch.float32).view(self.P, 12)
+
+    def point_list(self):
+        return self.view(self.layout.off_point_list, self.num_rendered * 4, torch.int32)
+
+    def ranges(self):
+        T = ((self.W + 15) // 16) * ((self.H + 15) // 16)
+        return self.view(self.layout.off_ranges, T * 8, torch.int32).view(T, 2)
+
+    def n_contrib(self):
+        return self.view(self.layout.off_n_contrib, self.H * self.W * 4, torch.int32).view(self.H, self.W)
+
+    def final_T(self):
+        return self.view(self.layout.off_final_T, self.H * self.W * 4, torch.float32).view(self.H, self.W)
+
+    def sorted_keys(self) -> torch.Tensor:
+        """Materialise the sorted 64-bit (tile<<32 | depth bits) keys (valid until the next call
+        on the same stream reuses the scratch block)."""
+        out = torch.empty(max(self.num_rendered, 1), dtype=torch.int64, device=self.block.device)
+        st = torch.cuda.current_stream(self.block.device).cuda_stream
+        _lib.check(_lib.load().gsb_debug_sorted_keys(self.P, self.H, self.W, self.block.data_ptr(),
+                                                     self.scratch.data_ptr(), self.d_cap, out.data_ptr(), st),
+                   "gsb_debug_sorted_keys")
+        return out[:self.num_rendered]
+
+
+def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D):
+    lib = _lib.load()
+    device = means3D.device
+    if device.type != "cuda":
+        raise ValueError("gaussianip_b200 runs on CUDA tensors only (no CPU fallback)")
+    P = means3D.shape[0]
+    H, W = int(rs.image_height), int(rs.image_width)
+    K = shs.shape[1] if shs is not None else 0
+    with torch.cuda.device(device):
+        ws = _workspace(device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        s, keep = _make_settings(rs, device)
+        color = torch.empty(3, H, W, dtype=torch.float32, device=device)
+        depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
+        alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
+        radii = torch.empty(P, dtype=torch.int32, device=device)
+        while True:
+            d_cap = ws.capacity_for(P)
+            L = _lib.layout(P, H, W, d_cap)
+            scratch = ws.ensure_scratch(L.scratch_bytes)
+            block = torch.empty(L.saved_bytes, dtype=torch.uint8, device=device)
+            rc = lib.gsb_forward(C.byref(s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(opacities),
+                                 _ptr(shs), _ptr(colors), _ptr(cov3D), radii.data_ptr(), color.data_ptr(),
+                                 depth.data_ptr(), alpha.data_ptr(), block.data_ptr(), scratch.data_ptr(), d_cap,
+                                 ws.binning_mode, ws.host_counts.data_ptr(), ws.event.cuda_event, stream)
+            _lib.check(rc, "gsb_forward")
+            ws.event.synchronize()          # waits for the 32-byte counts copy only
+            D = int(ws.host_counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
+            if D <= d_cap:
+                break
+            ws.d_cap = int(D * 1.25) + 4096   # outputs were not observable yet: enqueue again, larger
+            ws.retries += 1
+        ws.last_num_rendered = D
+        # follow the scene downwards slowly so one huge view does not pin memory forever
+        if D * 4 < ws.d_cap and ws.d_cap > max(1 << 16, 4 * P):
+            ws.d_cap = max(1 << 16, 4 * P, 2 * D)
+    sv = _Saved()
+    sv.block, sv.layout, sv.d_cap, sv.P, sv.K, sv.H, sv.W = block, L, d_cap, P, K, H, W
+    sv.num_rendered, sv.scratch, sv.settings_keep = D, scratch, keep
+    return color, radii, depth, alpha, sv
+
+
+def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
+                   g_color, g_depth, g_alpha, out=None, accumulate=False):
+    lib = _lib.load()
+    device = means3D.device
+    P, K, H, W = sv.P, sv.K, sv.H, sv.W
+    with torch.cuda.device(device):
+        ws = _workspace(device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        s, keep = _make_settings(rs, device)
+        scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
+
+        def grad_in(g, shape):
+            if g is None:
+                return torch.zeros(shape, dtype=torch.float32, device=device)
+            return g.to(dtype=torch.float32).contiguous()
+
+        g_color = grad_in(g_color, (3, H, W))
+        g_depth = grad_in(g_depth, (1, H, W))
+        g_alpha = grad_in(g_alpha, (1, H, W))
+        if out is None:
+            e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=device)
+            out = {"means3D": e(P, 3), "means2D": e(P, 3), "opacities": e(P, 1),
+                   "shs": e(P, K, 3) if shs is not None else None,
+                   "colors": e(P, 3) if colors is not None else None,
+                   "scales": e(P, 3) if scales is not None else None,
+                   "rotations": e(P, 4) if rotations is not None else None,
+                   "cov3D": e(P, 6) if cov3D is not None else None}
+        rc = lib.gsb_backward(C.byref(s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(opacities),
+                              _ptr(shs), _ptr(colors), _ptr(cov3D), radii.data_ptr(), sv.block.data_ptr(),
+                              scratch.data_ptr(), sv.d_cap, g_color.data_ptr(), g_depth.data_ptr(),
+                              g_alpha.data_ptr(), _ptr(out["means3D"]), _ptr(out["means2D"]), _ptr(out["shs"]),
+                              _ptr(out["colors"]), _ptr(out["opacities"]), _ptr(out["scales"]),
+                              _ptr(out["rotations"]), _ptr(out["cov3D"]), int(bool(accumulate)), stream)
+        _lib.check(rc, "gsb_backward")
+        del keep
+    return out
+
+
+def _prepare_inputs(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp):
+    none_if_empty = lambda t: None if (t is None or t.numel() == 0) else t
+    sh, colors_precomp = none_if_empty(sh), none_if_empty(colors_precomp)
+    scales, rotations, cov3Ds_precomp = none_if_empty(scales), none_if_empty(rotations), none_if_empty(cov3Ds_precomp)
+    device = means3D.device
+    means3D = _check(means3D, "means3D", (3,), device)
+    P = means3D.shape[0]
+    opacities = opacities.reshape(P, 1) if torch.is_tensor(opacities) and opacities.numel() == P else opacities
+    opacities = _check(opacities, "opacities", (1,), device)
+    if sh is not None:
+        if sh.dim() != 3 or sh.shape[2] != 3:
+            raise ValueError(f"shs must have shape [P, K, 3], got {tuple(sh.shape)}")
+        sh = _check(sh, "shs", tuple(sh.shape[1:]), device)
+    if colors_precomp is not None:
+        colors_precomp = _check(colors_precomp, "colors_precomp", (3,), device)
+    if scales is not None:
+        scales = _check(scales, "scales", (3,), device)
+    if rotations is not None:
+        rotations = _check(rotations, "rotations", (4,), device)
+    if cov3Ds_precomp is not None:
+        cov3Ds_precomp = _check(cov3Ds_precomp, "cov3D_precomp", (6,), device)
+    for name, t in (("shs", sh), ("colors_precomp", colors_precomp), ("scales", scales),
+                    ("rotations", rotations), ("cov3D_precomp", cov3Ds_precomp)):
+        if t is not None and t.shape[0] != P:
+            raise ValueError(f"{name} has {t.shape[0]} rows, means3D has {P}")
+    return means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = _prepare_inputs(
+            means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        color, radii, depth, alpha, sv = _forward_impl(raster_settings, means3D, sh, colors_precomp, opacities,
+                                                       scales, rotations, cov3Ds_precomp)
+        ctx.raster_settings = raster_settings
+        ctx.sv = sv
+        ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,
+                       cov3Ds_precomp is not None)
+        e = means3D.new_empty(0)
+        ctx.save_for_backward(means3D, sh if sh is not None else e,
+                              colors_precomp if colors_precomp is not None else e, opacities,
+                              scales if scales is not None else e, rotations if rotations is not None else e,
+                              cov3Ds_precomp if cov3Ds_precomp is not None else e, radii)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        means3D, sh, colors, opacities, scales, rotations, cov3D, radii = ctx.saved_tensors
+        has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
+        out = _backward_impl(ctx.raster_settings, ctx.sv, means3D, sh if has_sh else None,
+                             colors if has_col else None, opacities, scales if has_sc else None,
+                             rotations if has_rot else None, cov3D if has_cov else None, radii,
+                             grad_color, grad_depth, grad_alpha)
+        ctx.sv = None
+        return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
+                out["rotations"], out["cov3D"], None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """Boolean mask of points in front of the camera (view z > 0.2)."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            positions = _check(positions, "positions", (3,), positions.device)
+            if positions.device.type != "cuda":
+                raise ValueError("markVisible needs CUDA tensors (no CPU fallback)")
+            P = positions.shape[0]
+            view = _small(rs.viewmatrix, 16, "viewmatrix", positions.device)
+            proj = _small(rs.projmatrix, 16, "projmatrix", positions.device)
+            present = torch.empty(P, dtype=torch.uint8, device=positions.device)
+            with torch.cuda.device(positions.device):
+                st = torch.cuda.current_stream(positions.device).cuda_stream
+                _lib.check(_lib.load().gsb_mark_visible(P, positions.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                                                        present.data_ptr(), st), "gsb_mark_visible")
+            return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs)

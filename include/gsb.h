@@ -1,0 +1,180 @@
+/* gsb.h — C ABI of the B200-native Gaussian-splatting rasterizer (libgsb.so).
+ *
+ * This is the drop-in boundary for the one native operator GaussianIP calls:
+ * `diff_gaussian_rasterization._C` (external ashawkey depth+alpha fork; NOT vendored under
+ * /root/reference).  The reference binds that operator from Python at
+ *   gaussiansplatting/gaussian_renderer/__init__.py:14,36-51,85-93   (render)
+ *   gaussiansplatting/gaussian_renderer/__init__.py:124-139,175-183  (render_with_smaller_scale)
+ *   gaussiansplatting/gaussian_renderer/__init__.py:213-228,240-248  (render_deformed)
+ *   gs_renderer.py:10-13,943-958,992-1001                            (Renderer.render)
+ * Each entry point below names the `_C` function / stage it replaces.
+ *
+ * Conventions: plain C, raw DEVICE pointers and sizes, no torch types, `void* stream` is a
+ * cudaStream_t and always the last argument, every function returns 0 on success or a
+ * negative GSB_E_* code (never throws, never allocates or frees device memory, never
+ * synchronises the device unless `debug` is set in the settings).  All float tensors are
+ * contiguous fp32.  There is no CPU fallback.
+ */
+#ifndef GSB_H
+#define GSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1
+
+enum {
+  GSB_OK = 0,
+  GSB_E_INVALID = -1,     /* bad argument (null pointer, negative size, sh_degree > 3 ...) */
+  GSB_E_CUDA = -2,        /* a CUDA runtime call / kernel launch failed (see gsb_last_cuda_error) */
+  GSB_E_CAPACITY = -3,    /* D (num_rendered) exceeded D_cap; re-run with a larger workspace */
+  GSB_E_UNSUPPORTED = -4
+};
+
+/* The 12 fields of GaussianRasterizationSettings
+ * (gaussiansplatting/gaussian_renderer/__init__.py:36-49) that reach the kernels. */
+typedef struct GsbSettings {
+  int32_t image_height, image_width;
+  float tanfovx, tanfovy;
+  float scale_modifier;
+  int32_t sh_degree;         /* active degree, 0..3 */
+  int32_t prefiltered;       /* accepted for API parity; every call site passes False */
+  int32_t debug;             /* !=0: synchronise + check after every kernel */
+  const float* bg;           /* [3]  device */
+  const float* viewmatrix;   /* [16] device, column-major world->view (row-vector convention) */
+  const float* projmatrix;   /* [16] device, column-major full projection */
+  const float* campos;       /* [3]  device */
+} GsbSettings;
+
+/* Byte offsets of every sub-buffer inside the two blocks the HOST allocates per call
+ * (the library never allocates).  `saved` lives until the backward pass of the same view;
+ * `scratch` is transient within one call and may be shared by all calls on one stream. */
+typedef struct GsbLayout {
+  size_t saved_bytes;
+  size_t off_geom;        /* P x 48 B  GsbGeom record {x,y,conA,conB | conC,opacity,depth,r | g,b,extx,exty} */
+  size_t off_clamped;     /* P x u8    SH clamp mask (bit c: channel c clamped at 0) */
+  size_t off_counts;      /* 8 x u32   [0]=D (num_rendered) [1]=overflow flag [2]=#visible [3]=max tiles per Gaussian */
+  size_t off_point_list;  /* D_cap x u32  Gaussian index per sorted instance */
+  size_t off_ranges;      /* T x {u32 start,u32 end} */
+  size_t off_n_contrib;   /* H*W x u32 */
+  size_t off_final_T;     /* H*W x f32 */
+  size_t scratch_bytes;
+  size_t off_rect;        /* P x {u16 minx,miny,maxx,maxy} */
+  size_t off_tiles;       /* P x u32  tiles_touched */
+  size_t off_dkeys0;               /* P x u32  depth keys (0xFFFFFFFF when culled), kept intact */
+  size_t off_dkeys1, off_dkeys2;   /* P x u32  depth-sort ping/pong keys */
+  size_t off_didx0, off_didx1;     /* P x u32  depth-sort ping/pong Gaussian ids */
+  size_t off_offsets;     /* P x u32  exclusive scan of tiles_touched in emission order */
+  size_t off_blocksums;   /* scan partials */
+  size_t off_hist;        /* radix per-block digit histograms + digit totals */
+  size_t off_tkeys0, off_tkeys1;   /* D_cap x u32 tile ids ping/pong */
+  size_t off_tvals_alt;   /* D_cap x u32 */
+  size_t off_keys64_0, off_keys64_1; /* D_cap x u64 (tile<<32|depth) keys, flat-64 mode + debug */
+  size_t off_ggrad;       /* P x 48 B  per-Gaussian gradient record written by render_bwd */
+} GsbLayout;
+
+int gsb_abi_version(void);
+const char* gsb_strerror(int code);
+/* Text of the last CUDA error seen by this thread ("" if none). */
+const char* gsb_last_cuda_error(void);
+
+/* Workspace sizing (replaces the resize callbacks `_C.rasterize_gaussians` receives for
+ * geomBuffer / binningBuffer / imgBuffer).  D_cap is the instance capacity. */
+int gsb_layout(int P, int H, int W, long long D_cap, GsbLayout* out);
+
+/* Binning modes for gsb_bin_sort / gsb_forward. */
+#define GSB_BIN_TWO_LEVEL 0   /* 32-bit depth sort of P Gaussians + stable tile partition of D instances */
+#define GSB_BIN_FLAT64    1   /* duplicateWithKeys + 64-bit (tile|depth) LSD radix sort (reference structure) */
+
+/* Stage 1 — replaces preprocessCUDA + InclusiveSum inside `_C.rasterize_gaussians`.
+ * Exactly one of shs / colors_precomp, and exactly one of (scales, rotations) /
+ * cov3D_precomp, is non-null.  K = coefficients per Gaussian present in `shs` ([P,K,3]). */
+int gsb_preprocess_fwd(const GsbSettings* s, int P, int K,
+                       const float* means3D, const float* scales, const float* rotations,
+                       const float* opacities, const float* shs, const float* colors_precomp,
+                       const float* cov3D_precomp,
+                       int32_t* radii_out, void* saved, void* scratch, long long D_cap,
+                       void* stream);
+
+/* Stage 2 — replaces duplicateWithKeys + cub::DeviceRadixSort::SortPairs +
+ * identifyTileRanges.  Result: saved.point_list, saved.ranges, saved.counts.
+ * Where the reference synchronises the device to read num_rendered, this library copies
+ * saved.counts (8 x u32) to `host_counts` (pinned host memory, may be null) right after the
+ * scan and records `event` (a cudaEvent_t, may be null) behind that copy: the host can wait on
+ * the event alone, while the sort and blend kernels are already queued. */
+int gsb_bin_sort(const GsbSettings* s, int P, void* saved, void* scratch, long long D_cap,
+                 int mode, uint32_t* host_counts, void* event, void* stream);
+
+/* Stage 3 — replaces renderCUDA (forward).  Outputs [3,H,W], [1,H,W], [1,H,W]. */
+int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap,
+                   float* out_color, float* out_depth, float* out_alpha, void* stream);
+
+/* Stages 1-3 in one call — replaces `_C.rasterize_gaussians`. */
+int gsb_forward(const GsbSettings* s, int P, int K,
+                const float* means3D, const float* scales, const float* rotations,
+                const float* opacities, const float* shs, const float* colors_precomp,
+                const float* cov3D_precomp,
+                int32_t* radii_out, float* out_color, float* out_depth, float* out_alpha,
+                void* saved, void* scratch, long long D_cap, int mode,
+                uint32_t* host_counts, void* event, void* stream);
+
+/* Asynchronously copy saved.counts (8 x u32) to `host_dst` (pinned host memory). */
+int gsb_read_counts(const void* saved, int P, int H, int W, long long D_cap,
+                    uint32_t* host_dst, void* stream);
+
+/* Backward stage 1 — replaces renderCUDA (backward): per-pixel reverse blend, gradients
+ * reduced across each warp before one atomic per (warp, Gaussian, component). */
+int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch, long long D_cap,
+                   const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                   void* stream);
+
+/* Backward stage 2 — replaces computeCov2DCUDA + preprocessCUDA (backward).  Output
+ * pointers may be null when the matching input was not given.  accumulate != 0 adds into
+ * the outputs (beta = 1) instead of overwriting, so several views can share one gradient
+ * bucket that is then all-reduced once. */
+int gsb_preprocess_bwd(const GsbSettings* s, int P, int K,
+                       const float* means3D, const float* scales, const float* rotations,
+                       const float* opacities, const float* shs, const float* colors_precomp,
+                       const float* cov3D_precomp, const int32_t* radii,
+                       const void* saved, const void* scratch, long long D_cap,
+                       float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs,
+                       float* dL_dcolors, float* dL_dopacities, float* dL_dscales,
+                       float* dL_drotations, float* dL_dcov3D, int accumulate, void* stream);
+
+/* Both backward stages — replaces `_C.rasterize_gaussians_backward`. */
+int gsb_backward(const GsbSettings* s, int P, int K,
+                 const float* means3D, const float* scales, const float* rotations,
+                 const float* opacities, const float* shs, const float* colors_precomp,
+                 const float* cov3D_precomp, const int32_t* radii,
+                 const void* saved, void* scratch, long long D_cap,
+                 const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs,
+                 float* dL_dcolors, float* dL_dopacities, float* dL_dscales,
+                 float* dL_drotations, float* dL_dcov3D, int accumulate, void* stream);
+
+/* Replaces `_C.mark_visible` (GaussianRasterizer.markVisible): present[i] = view z > 0.2. */
+int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Test / measurement helpers. */
+/* Materialise the sorted 64-bit (tile<<32 | depth bits) key of every instance. */
+int gsb_debug_sorted_keys(int P, int H, int W, const void* saved, const void* scratch,
+                          long long D_cap, uint64_t* keys_out, void* stream);
+/* Stable LSD radix sort of n (key,value) pairs on bits [0,end_bit); result in keys_out/vals_out.
+ * `tmp` must hold gsb_radix_tmp_bytes(n, key_bytes). */
+size_t gsb_radix_tmp_bytes(long long n, int key_bytes);
+int gsb_radix_sort_pairs_u32(long long n, const uint32_t* keys_in, const uint32_t* vals_in,
+                             uint32_t* keys_out, uint32_t* vals_out, int end_bit, void* tmp,
+                             void* stream);
+int gsb_radix_sort_pairs_u64(long long n, const uint64_t* keys_in, const uint32_t* vals_in,
+                             uint64_t* keys_out, uint32_t* vals_out, int end_bit, void* tmp,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB_H */

@@ -1,0 +1,237 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): bit-exact radii / sort keys / tile ranges / instance order /
+per-pixel contributor counts; forward colour, depth, alpha within 1e-5 absolute (fp32);
+gradients within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FWD_ATOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _gpu_forward_state(scene, device, mode="two_level"):
+    from gaussianip_b200 import rasterizer as R
+    R.set_binning_mode(mode, device)
+    inp = scene.inputs(device)
+    rs = R.GaussianRasterizationSettings(scene.H, scene.W, scene.tanfovx, scene.tanfovy, scene.bg.to(device),
+                                         scene.scale_modifier, scene.viewmatrix.to(device),
+                                         scene.projmatrix.to(device), scene.sh_degree, scene.campos.to(device),
+                                         False, True)
+    m3, sh, col, op, sc, rot, cov = R._prepare_inputs(inp["means3D"], inp["means2D"], inp["shs"], inp["colors"],
+                                                      inp["opacities"], inp["scales"], inp["rotations"], inp["cov3D"])
+    color, radii, depth, alpha, sv = R._forward_impl(rs, m3, sh, col, op, sc, rot, cov)
+    keys = sv.sorted_keys().cpu().numpy().view(np.uint64)
+    R.set_binning_mode("two_level", device)
+    return color, radii, depth, alpha, sv, keys
+
+
+def _grad_close(name, got, ref, rtol=GRAD_RTOL):
+    got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    # relative to the tensor's largest gradient (atomic accumulation order differs per element)
+    assert err <= rtol * max(scale, 1e-12), f"{name}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+SCENES = {
+    "sh0_small": dict(P=3000, H=128, W=128, sh_degree=0),
+    "sh0_nonsquare_ragged": dict(P=3000, H=100, W=150, sh_degree=0, bg=(0.3, 0.6, 0.9)),
+    "sh3": dict(P=2500, H=96, W=96, sh_degree=3, bg=(1.0, 1.0, 1.0)),
+    "sh1_in_sh3_storage": dict(P=2000, H=96, W=96, sh_degree=1, K=16),
+    "big_splats": dict(P=1500, H=128, W=128, sh_degree=0, scale_boost=6.0),
+    "precomp_color_cov": dict(P=2000, H=96, W=96, sh_degree=0, precomp_color=True, precomp_cov=True),
+    "scale_modifier": dict(P=2000, H=96, W=96, sh_degree=2, scale_modifier=1.7),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("mode", ["two_level", "flat64"])
+def test_forward_exact_and_tolerance(cuda_device, name, mode):
+    scene = util.humanoid_scene(**SCENES[name])
+    ref = util.run_oracle(scene)
+    color, radii, depth, alpha, sv, keys = _gpu_forward_state(scene, cuda_device, mode)
+    g, b, img = ref["geom"], ref["binning"], ref["image"]
+    # bit-exact integer / index results
+    assert torch.equal(radii.cpu(), g.radii), "radii differ"
+    assert sv.num_rendered == len(b.keys), f"num_rendered {sv.num_rendered} vs {len(b.keys)}"
+    assert np.array_equal(keys, b.keys), "sorted (tile|depth) keys differ"
+    assert np.array_equal(sv.point_list().cpu().numpy().astype(np.int64), b.point_list), "instance order differs"
+    assert np.array_equal(sv.ranges().cpu().numpy().astype(np.int64), b.ranges), "tile ranges differ"
+    # per-Gaussian records: bit-exact where the oracle mirrors the op order
+    geom = sv.geom().cpu()
+    vis = g.visible
+    assert torch.equal(geom[vis][:, 0:2], g.xy[vis]), "pixel centres differ"
+    assert torch.equal(geom[vis][:, 6], g.depth[vis]), "depths differ"
+    torch.testing.assert_close(geom[vis][:, [2, 3, 4]], g.conic[vis], rtol=1e-6, atol=0)
+    torch.testing.assert_close(geom[vis][:, [7, 8, 9]], g.rgb[vis], rtol=1e-5, atol=1e-6)
+    # images
+    assert (color.cpu() - ref["color"]).abs().max().item() <= FWD_ATOL
+    assert (depth.cpu() - ref["depth"]).abs().max().item() <= FWD_ATOL
+    assert (alpha.cpu() - ref["alpha"]).abs().max().item() <= FWD_ATOL
+    # contributor counts: exact, except pixels where the oracle itself flags a threshold decision
+    # (alpha >= 1/255 or T < 1e-4) that sits inside fp32 exp/rounding noise
+    nc = sv.n_contrib().cpu()
+    mism = (nc != img.n_contrib) & ~img.marginal
+    assert int(mism.sum()) == 0, f"{int(mism.sum())} unflagged n_contrib mismatches"
+    assert float(img.marginal.float().mean()) < 0.05
+    ok = ~img.marginal
+    torch.testing.assert_close(sv.final_T().cpu()[ok], img.final_T[ok], rtol=2e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_backward_tolerance(cuda_device, name):
+    scene = util.humanoid_scene(**SCENES[name])
+    w = util.loss_weights(scene.H, scene.W)
+    ref = util.run_oracle(scene, grads=w, requires_grad=True)
+    got = util.run_gpu(scene, cuda_device, grads=w, requires_grad=True, debug=True)
+    for k, rg in ref["grads"].items():
+        if rg is None:
+            continue
+        gg = got["grads"][k]
+        assert gg is not None, f"no gradient for {k}"
+        _grad_close(k, gg, rg)
+    # means2D grad is (x, y, 0)
+    assert float(got["grads"]["means2D"][:, 2].abs().max()) == 0.0
+    # culled Gaussians get exactly zero gradient
+    culled = (got["radii"] == 0)
+    if bool(culled.any()):
+        assert float(got["grads"]["means3D"][culled].abs().max()) == 0.0
+
+
+def test_grad_linearity_and_inf_propagation(cuda_device):
+    """AMP: the op must be exactly linear in incoming grads and propagate inf (GradScaler)."""
+    scene = util.humanoid_scene(P=1500, H=64, W=64, sh_degree=0)
+    w = util.loss_weights(64, 64)
+    a = util.run_gpu(scene, cuda_device, grads=w, requires_grad=True)
+    w2 = tuple(t * 65536.0 for t in w)
+    b = util.run_gpu(scene, cuda_device, grads=w2, requires_grad=True)
+    for k in ("means3D", "opacities", "scales", "rotations", "shs", "means2D"):
+        _grad_close(k, b["grads"][k] / 65536.0, a["grads"][k], rtol=1e-5)
+    w3 = (w[0].clone(), w[1], w[2])
+    w3[0][:, 32, 32] = float("inf")
+    c = util.run_gpu(scene, cuda_device, grads=w3, requires_grad=True)
+    assert not bool(torch.isfinite(c["grads"]["means3D"]).all())
+
+
+def test_cross_path_python_twins(cuda_device):
+    """op(shs) == op(colors_precomp = python SH twin); op(scales, rotations) == op(cov3D twin)
+    (the reference's convert_SHs_python / compute_cov3D_python switches,
+    gaussian_renderer/__init__.py:62-63,73-78)."""
+    from oracle import splat_torch as O
+    scene = util.humanoid_scene(P=2500, H=96, W=96, sh_degree=2)
+    base = util.run_gpu(scene, cuda_device)
+    d = scene.means3D - scene.campos[None]
+    dirs = d / d.norm(dim=1, keepdim=True)
+    colors = torch.clamp_min(O.eval_sh_rgb(2, scene.shs, dirs) + 0.5, 0.0)
+    cov = O.cov3d_from_scale_rot(scene.scales, scene.rotations, 1.0)
+    import dataclasses
+    twin = dataclasses.replace(scene, shs=None, colors=colors, scales=None, rotations=None, cov3D=cov)
+    alt = util.run_gpu(twin, cuda_device)
+    assert torch.equal(base["radii"], alt["radii"])
+    for k in ("color", "depth", "alpha"):
+        assert (base[k] - alt[k]).abs().max().item() <= FWD_ATOL
+
+
+def test_closed_form_single_gaussian(cuda_device):
+    """One isotropic Gaussian on the optical axis: centre alpha = min(0.99, o),
+    colour = alpha*c + (1-alpha)*bg, depth = alpha*z, radius = ceil(3*sqrt(sigma_px^2+0.3))."""
+    import math
+    from gaussianip_b200 import rasterizer as R
+    from gaussianip_b200.cameras import Camera, look_at_c2w
+    H = W = 65
+    cam = Camera(look_at_c2w((2.0, 0.0, 0.0)), math.radians(60), H, W, data_device=cuda_device)
+    s, o, z = 0.02, 0.8, 2.0
+    dev = cuda_device
+    rs = R.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, torch.tensor([0.1, 0.2, 0.3], device=dev),
+                                         1.0, cam.world_view_transform, cam.full_proj_transform, 0,
+                                         cam.camera_center, False, False)
+    col = torch.tensor([[0.9, 0.5, 0.2]], device=dev)
+    out = R.GaussianRasterizer(rs)(means3D=torch.zeros(1, 3, device=dev), means2D=torch.zeros(1, 3, device=dev),
+                                   opacities=torch.tensor([[o]], device=dev), colors_precomp=col,
+                                   scales=torch.full((1, 3), s, device=dev),
+                                   rotations=torch.tensor([[1.0, 0, 0, 0]], device=dev))
+    color, radii, depth, alpha = out
+    focal = W / (2 * cam.tanfovx)
+    sigma2 = (s * focal / z) ** 2 + 0.3
+    assert int(radii[0]) == math.ceil(3 * math.sqrt(sigma2))
+    c = H // 2
+    assert abs(float(alpha[0, c, c]) - o) < 1e-5
+    assert abs(float(depth[0, c, c]) - o * z) < 1e-5
+    exp = o * col[0].cpu() + (1 - o) * torch.tensor([0.1, 0.2, 0.3])
+    assert (color[:, c, c].cpu() - exp).abs().max().item() < 1e-5
+    # far corner sees only background
+    assert (color[:, 0, 0].cpu() - torch.tensor([0.1, 0.2, 0.3])).abs().max().item() < 1e-6
+
+
+def test_empty_and_all_culled(cuda_device):
+    from gaussianip_b200 import rasterizer as R
+    scene = util.humanoid_scene(P=500, H=64, W=64, sh_degree=0, bg=(0.2, 0.4, 0.6))
+    # all Gaussians behind the camera: flip the view direction by mirroring the cloud
+    import dataclasses
+    far = dataclasses.replace(scene, means3D=scene.means3D + 100.0 * (scene.campos / scene.campos.norm())[None])
+    got = util.run_gpu(far, cuda_device, grads=util.loss_weights(64, 64), requires_grad=True)
+    assert int((got["radii"] > 0).sum()) == 0
+    assert torch.allclose(got["color"].cpu(), torch.tensor([0.2, 0.4, 0.6]).view(3, 1, 1).expand(3, 64, 64))
+    assert float(got["alpha"].abs().max()) == 0.0
+    assert float(got["grads"]["means3D"].abs().max()) == 0.0
+    # P = 0
+    dev = cuda_device
+    rs = R.GaussianRasterizationSettings(32, 32, 0.5, 0.5, torch.zeros(3, device=dev), 1.0,
+                                         torch.eye(4, device=dev), torch.eye(4, device=dev), 0,
+                                         torch.zeros(3, device=dev), False, False)
+    e = lambda *s: torch.zeros(*s, device=dev)
+    color, radii, depth, alpha = R.GaussianRasterizer(rs)(means3D=e(0, 3), means2D=e(0, 3), opacities=e(0, 1),
+                                                          colors_precomp=e(0, 3), scales=e(0, 3), rotations=e(0, 4))
+    assert radii.numel() == 0 and float(color.abs().max()) == 0.0
+
+
+def test_argument_errors(cuda_device):
+    from gaussianip_b200 import rasterizer as R
+    dev = cuda_device
+    rs = R.GaussianRasterizationSettings(32, 32, 0.5, 0.5, torch.zeros(3, device=dev), 1.0,
+                                         torch.eye(4, device=dev), torch.eye(4, device=dev), 0,
+                                         torch.zeros(3, device=dev), False, False)
+    r = R.GaussianRasterizer(rs)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=z(4, 3), means2D=z(4, 3), opacities=z(4, 1), scales=z(4, 3), rotations=z(4, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=z(4, 3), means2D=z(4, 3), opacities=z(4, 1), colors_precomp=z(4, 3), scales=z(4, 3))
+    with pytest.raises(ValueError):
+        r(means3D=z(4, 2), means2D=z(4, 3), opacities=z(4, 1), colors_precomp=z(4, 3), scales=z(4, 3),
+          rotations=z(4, 4))
+    with pytest.raises(ValueError):
+        r(means3D=torch.zeros(4, 3), means2D=torch.zeros(4, 3), opacities=torch.zeros(4, 1),
+          colors_precomp=torch.zeros(4, 3), scales=torch.zeros(4, 3), rotations=torch.zeros(4, 4))
+
+
+def test_mark_visible(cuda_device):
+    from gaussianip_b200 import rasterizer as R
+    scene = util.humanoid_scene(P=800, H=64, W=64)
+    dev = cuda_device
+    rs = R.GaussianRasterizationSettings(64, 64, scene.tanfovx, scene.tanfovy, scene.bg.to(dev), 1.0,
+                                         scene.viewmatrix.to(dev), scene.projmatrix.to(dev), 0,
+                                         scene.campos.to(dev), False, False)
+    vis = R.GaussianRasterizer(rs).markVisible(scene.means3D.to(dev)).cpu()
+    ref = util.run_oracle(scene)["geom"].depth > 0.2
+    assert torch.equal(vis, ref)
+
+
+def test_capacity_growth_retry(cuda_device):
+    """A view whose D exceeds the instance capacity is transparently re-enqueued."""
+    from gaussianip_b200 import rasterizer as R
+    scene = util.humanoid_scene(P=20000, H=128, W=128, sh_degree=0, scale_boost=10.0)
+    ws = R._workspace(cuda_device)
+    ws.d_cap = 1 << 16
+    before = ws.retries
+    got = util.run_gpu(scene, cuda_device)
+    ref = util.run_oracle(scene)
+    assert len(ref["binning"].keys) > (1 << 16)
+    assert ws.retries == before + 1
+    assert (got["color"].cpu() - ref["color"]).abs().max().item() <= FWD_ATOL
