@@ -51,6 +51,9 @@ _PROTOS = {
     "gsb_render_bwd": (C.c_int, [C.POINTER(GsbSettings), C.c_int, _P, _P, C.c_longlong, _P, _P, _P, _P]),
     "gsb_preprocess_bwd": (C.c_int, [C.POINTER(GsbSettings), C.c_int, C.c_int] + [_P] * 8 + [_P, _P, C.c_longlong] + [_P] * 8 + [C.c_int, _P]),
     "gsb_backward": (C.c_int, [C.POINTER(GsbSettings), C.c_int, C.c_int] + [_P] * 8 + [_P, _P, C.c_longlong] + [_P] * 3 + [_P] * 8 + [C.c_int, _P]),
+    "gsb_profile_enable": (C.c_int, [C.c_int]),
+    "gsb_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "gsb_launch_count": (C.c_longlong, []),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "gsb_debug_sorted_keys": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.c_longlong, _P, _P]),
     "gsb_radix_tmp_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
@@ -95,3 +98,23 @@ def layout(P: int, H: int, W: int, D_cap: int) -> GsbLayout:
     L = GsbLayout()
     check(load().gsb_layout(P, H, W, D_cap, C.byref(L)), "gsb_layout")
     return L
+
+
+STAGES = ("preprocess_fwd", "depth_sort", "scan_emit", "tile_sort", "ranges", "render_fwd", "render_bwd",
+          "preprocess_bwd")
+
+
+def profile_enable(on: bool) -> None:
+    check(load().gsb_profile_enable(int(on)), "gsb_profile_enable")
+
+
+def profile_read():
+    """{stage: (total device ms, calls)} accumulated since profile_enable(True)."""
+    ms = (C.c_float * len(STAGES))()
+    calls = (C.c_int * len(STAGES))()
+    check(load().gsb_profile_read(ms, calls), "gsb_profile_read")
+    return {s: (float(ms[i]), int(calls[i])) for i, s in enumerate(STAGES)}
+
+
+def launch_count() -> int:
+    return int(load().gsb_launch_count())

@@ -3,6 +3,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -12,6 +16,44 @@ static thread_local char g_cuda_err[256] = "";
 int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
   return GSB_E_CUDA;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- stage profiler ------------------------------------------------------------------------
+namespace {
+struct ProfRec { int stage; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;      // recorded, not yet resolved
+std::vector<cudaEvent_t> g_prof_pool;  // reusable events
+cudaEvent_t g_prof_open[GSB_NUM_STAGES];
+double g_prof_ms[GSB_NUM_STAGES];
+int g_prof_calls[GSB_NUM_STAGES];
+cudaEvent_t prof_get_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e = prof_get_event();
+  cudaEventRecord(e, st);
+  g_prof_open[stage] = e;
+}
+void prof_end(int stage, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_open[stage]) return;
+  cudaEvent_t e = prof_get_event();
+  cudaEventRecord(e, st);
+  g_prof_recs.push_back({stage, g_prof_open[stage], e});
+  g_prof_open[stage] = nullptr;
 }
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -81,6 +123,33 @@ const char* gsb_strerror(int code) {
 
 const char* gsb_last_cuda_error(void) { return g_cuda_err; }
 
+int gsb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof_recs.clear();
+  for (int i = 0; i < GSB_NUM_STAGES; ++i) { g_prof_ms[i] = 0.0; g_prof_calls[i] = 0; g_prof_open[i] = nullptr; }
+  g_prof_on = on != 0;
+  return GSB_OK;
+}
+
+int gsb_profile_read(float* ms_out, int* calls_out) {
+  if (!ms_out || !calls_out) return GSB_E_INVALID;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) {
+    GSB_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    GSB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    g_prof_ms[r.stage] += ms;
+    g_prof_calls[r.stage] += 1;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+  for (int i = 0; i < GSB_NUM_STAGES; ++i) { ms_out[i] = (float)g_prof_ms[i]; calls_out[i] = g_prof_calls[i]; }
+  return GSB_OK;
+}
+
+long long gsb_launch_count(void) { return g_launches.load(); }
+
 int gsb_layout(int P, int H, int W, long long D_cap, GsbLayout* out) { return layout(P, H, W, D_cap, out); }
 
 int gsb_preprocess_fwd(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
@@ -97,6 +166,7 @@ int gsb_preprocess_fwd(const GsbSettings* s, int P, int K, const float* means3D,
   int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
   if (rc) return rc;
   const View v = make_view(s);
+  ProfScope ps(GSB_STAGE_PREPROCESS_FWD, (cudaStream_t)stream);
   return launch_preprocess_fwd(v, P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
                                cov3D_precomp, radii_out, at<Geom>(saved, L.off_geom),
                                at<uint8_t>(saved, L.off_clamped), at<ushort4>(scratch, L.off_rect),
@@ -121,6 +191,7 @@ int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap, fl
   GsbLayout L;
   int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
   if (rc) return rc;
+  ProfScope ps(GSB_STAGE_RENDER_FWD, (cudaStream_t)stream);
   return launch_render_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), out_color, out_depth, out_alpha,
                            at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
@@ -158,6 +229,7 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
   GsbLayout L;
   int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
   if (rc) return rc;
+  ProfScope ps(GSB_STAGE_RENDER_BWD, (cudaStream_t)stream);
   return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_n_contrib),
                            at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
@@ -184,6 +256,7 @@ int gsb_preprocess_bwd(const GsbSettings* s, int P, int K, const float* means3D,
   GsbLayout L;
   int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
   if (rc) return rc;
+  ProfScope ps(GSB_STAGE_PREPROCESS_BWD, (cudaStream_t)stream);
   return launch_preprocess_bwd(make_view(s), P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
                                cov3D_precomp, radii, at<Geom>(saved, L.off_geom),
                                at<uint8_t>(saved, L.off_clamped), at<GGrad>(scratch, L.off_ggrad), dL_dmeans3D,

@@ -376,8 +376,11 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     uint32_t* vA = at<uint32_t>(scratch, L.off_didx0);
     uint32_t* kB = at<uint32_t>(scratch, L.off_dkeys2);
     uint32_t* vB = at<uint32_t>(scratch, L.off_didx1);
+    prof_begin(GSB_STAGE_DEPTH_SORT, st);
     rc = radix_sort_pairs<uint32_t>(P, nullptr, dkeys, nullptr, kA, vA, kB, vB, 32, true, hist, debug, st);
+    prof_end(GSB_STAGE_DEPTH_SORT, st);
     if (rc) return rc;
+    prof_begin(GSB_STAGE_SCAN_EMIT, st);
     const uint32_t* order = vB;  // 4 passes -> result in B
     // (2) offsets in that order, D, overflow flag
     tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums);
@@ -394,15 +397,20 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     emit_kernel<0><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums, rect, dkeys, v.gx, D_cap, tkB,
                                                      nullptr, tvB);
     GSB_POST_LAUNCH(debug, st, "emit_kernel");
+    prof_end(GSB_STAGE_SCAN_EMIT, st);
+    prof_begin(GSB_STAGE_TILE_SORT, st);
     rc = radix_sort_pairs<uint32_t>(D_cap, counts + CNT_D, tkB, tvB, tkA, tvA, tkB, tvB, tile_bits, false, hist,
                                     debug, st);
+    prof_end(GSB_STAGE_TILE_SORT, st);
     if (rc) return rc;
+    ProfScope pr(GSB_STAGE_RANGES, st);
     // (a single-tile image needs 0 passes: the emitted order in B is already final)
     tile_ranges_kernel<uint32_t><<<cap_blocks, 256, 0, st>>>(inA ? tkA : tkB, counts + CNT_D, D_cap, ranges);
     GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
     return GSB_OK;
   }
   if (mode == GSB_BIN_FLAT64) {
+    prof_begin(GSB_STAGE_SCAN_EMIT, st);
     tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums);
     GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
     scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode);
@@ -417,9 +425,13 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     emit_kernel<1><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums, rect, dkeys, v.gx, D_cap,
                                                      nullptr, kB, tvB);
     GSB_POST_LAUNCH(debug, st, "emit_kernel");
+    prof_end(GSB_STAGE_SCAN_EMIT, st);
+    prof_begin(GSB_STAGE_TILE_SORT, st);
     rc = radix_sort_pairs<uint64_t>(D_cap, counts + CNT_D, kB, tvB, kA, tvA, kB, tvB, end_bit, false, hist, debug,
                                     st);
+    prof_end(GSB_STAGE_TILE_SORT, st);
     if (rc) return rc;
+    ProfScope pr(GSB_STAGE_RANGES, st);
     tile_ranges_kernel<uint64_t><<<cap_blocks, 256, 0, st>>>(inA ? kA : kB, counts + CNT_D, D_cap, ranges);
     GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
     return GSB_OK;

@@ -64,6 +64,15 @@ inline const T* at(const void* base, size_t off) {
 
 // error plumbing (api.cu)
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();
+// stage timing (api.cu): no-ops unless gsb_profile_enable(1)
+void prof_begin(int stage, cudaStream_t st);
+void prof_end(int stage, cudaStream_t st);
+struct ProfScope {
+  int stage; cudaStream_t st;
+  ProfScope(int s, cudaStream_t t) : stage(s), st(t) { prof_begin(stage, st); }
+  ~ProfScope() { prof_end(stage, st); }
+};
 #define GSB_CUDA(call)                                          \
   do {                                                          \
     cudaError_t e__ = (call);                                   \
@@ -73,6 +82,7 @@ int cuda_fail(cudaError_t e, const char* what);
 #define GSB_POST_LAUNCH(dbg, st, name)                                              \
   do {                                                                              \
     cudaError_t e__ = cudaGetLastError();                                           \
+    gsb::count_launch();                                                            \
     if (e__ == cudaSuccess && (dbg)) e__ = cudaStreamSynchronize(st);               \
     if (e__ != cudaSuccess) return gsb::cuda_fail(e__, name);                       \
   } while (0)

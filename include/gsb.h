@@ -160,6 +160,21 @@ int gsb_backward(const GsbSettings* s, int P, int K,
 int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
 
+/* Measurement: per-stage device timing and launch counting, live, inside the normal call path.
+ * While enabled the library records a cudaEvent on the caller's stream at every stage
+ * boundary of gsb_forward / gsb_backward (about 1 us of host time each). */
+enum {
+  GSB_STAGE_PREPROCESS_FWD = 0, GSB_STAGE_DEPTH_SORT = 1, GSB_STAGE_SCAN_EMIT = 2,
+  GSB_STAGE_TILE_SORT = 3, GSB_STAGE_RANGES = 4, GSB_STAGE_RENDER_FWD = 5,
+  GSB_STAGE_RENDER_BWD = 6, GSB_STAGE_PREPROCESS_BWD = 7, GSB_NUM_STAGES = 8
+};
+int gsb_profile_enable(int on);                   /* resets the accumulators */
+/* Synchronises the recorded events; ms_out[GSB_NUM_STAGES] = summed device ms per stage,
+ * calls_out[GSB_NUM_STAGES] = number of times each stage ran since gsb_profile_enable(1). */
+int gsb_profile_read(float* ms_out, int* calls_out);
+/* Kernels launched by this library (host-side counter, all threads) since process start. */
+long long gsb_launch_count(void);
+
 /* Test / measurement helpers. */
 /* Materialise the sorted 64-bit (tile<<32 | depth bits) key of every instance. */
 int gsb_debug_sorted_keys(int P, int H, int W, const void* saved, const void* scratch,
