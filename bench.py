@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Headline benchmark: fwd+bwd views/s of the Gaussian-splatting rasterizer at 1 M Gaussians,
+4 x 1024^2 AHDS orbit views per step per GPU (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one optimisation step's worth of rendering: every rank renders `views` random
+orbit views of the shared 1 M-Gaussian humanoid (colour + depth + alpha), back-propagates a
+dense synthetic loss through the operator and the parameter activations, then (N > 1) the
+flat gradient bucket and the radii are all-reduced with NCCL.  `value` = views of all ranks /
+device time (CUDA events, max over ranks), inputs resident in HBM.  `e2e` = the same step
+through the public render() API starting from pinned HOST parameter buffers, with the
+host->device copies and the device->host loss read inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "fwd+bwd views/s @1024^2, 1M Gaussians (4-view AHDS batch per GPU)"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--views", type=int, default=4, help="views per step per GPU")
+    ap.add_argument("--sh-degree", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"AHDS stage-1 shape: {a.points} Gaussians (capsule humanoid, seed 0), SH deg {a.sh_degree}, "
+            f"{a.views} random orbit views/GPU/step at {a.res}x{a.res}, colour+depth+alpha fwd+bwd")
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- reference arm: the oracle's CPU evaluation of the identical math -------------------------
+
+def cpu_reference_run(a, steps, warmup, budget_s):
+    """Times oracle/splat_torch.py (pure PyTorch fp32, all host threads) on a bounded sample of
+    the bench workload: per step one view, full preprocess + binning of all Gaussians, blending
+    + autograd backward of every `stride`-th tile row.  views/s = (fraction of the view's
+    instances that were blended) / step time."""
+    from oracle import splat_torch as O
+    from gaussianip_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cl = synthetic.make_cloud(a.points, a.sh_degree, 0)
+    cams = synthetic.ahds_cameras(a.views, a.res, a.res, seed=1, device="cpu")
+    g = torch.Generator().manual_seed(2)
+    w = (torch.randn(3, a.res, a.res, generator=g), torch.randn(1, a.res, a.res, generator=g),
+         torch.randn(1, a.res, a.res, generator=g))
+    tile_rows_total = (a.res + 15) // 16
+
+    def one(view, stride, phase):
+        cam = cams[view % len(cams)]
+        st = O.Settings(a.res, a.res, cam.tanfovx, cam.tanfovy, torch.zeros(3), 1.0, cam.world_view_transform,
+                        cam.full_proj_transform, a.sh_degree, cam.camera_center)
+        leaves = [t.clone().requires_grad_(True) for t in (cl.xyz, cl.features_dc, cl.features_rest, cl.scaling,
+                                                            cl.rotation, cl.opacity)]
+        xyz, fdc, frest, sc, rot, op = leaves
+        m2d = torch.zeros_like(xyz, requires_grad=True)
+        t0 = time.perf_counter()
+        out = O.rasterize(st, xyz, m2d, torch.sigmoid(op), shs=torch.cat((fdc, frest), 1), scales=torch.exp(sc),
+                          rotations=torch.nn.functional.normalize(rot), return_aux=True,
+                          tile_rows=(phase, stride))
+        color, radii, depth, alpha, geom, binning, img = out
+        ((color * w[0]).sum() + (depth * w[1]).sum() + (alpha * w[2]).sum()).backward()
+        dt = time.perf_counter() - t0
+        rng = binning.ranges
+        rows = torch.arange(rng.shape[0]) // binning.grid[0]
+        sel = (rows % stride) == phase
+        frac = float((rng[:, 1] - rng[:, 0])[sel.numpy()].sum()) / max(1, len(binning.keys))
+        return dt, frac
+
+    # probe with a sparse sample to size the real one
+    stride = max(1, tile_rows_total // 4)
+    dt, frac = one(0, stride, 0)
+    est_full = dt / max(frac, 1e-6) * 0.9
+    per_step_budget = budget_s / max(1, steps + warmup)
+    stride = 1
+    while stride < tile_rows_total and est_full / stride > per_step_budget:
+        stride *= 2
+    times, fracs = [], []
+    for i in range(warmup + steps):
+        dt, frac = one(i, stride, i % stride)
+        if i >= warmup:
+            times.append(dt); fracs.append(frac)
+    vps = sum(fracs) / sum(times)
+    sample = (f"{steps} steps x 1 view: full preprocess+binning of {a.points} Gaussians, blend+backward of every "
+              f"{stride}-th tile row ({100 * sum(fracs) / len(fracs):.1f}% of the view's instances per step), "
+              f"{sum(times):.1f} s CPU wall; views/s = blended instance fraction / time")
+    return vps, cores, sample, sum(times) / len(times) * 1e3
+
+
+# ---- our arm -----------------------------------------------------------------------------------------------
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warmup = max(1, a.steps), max(0, min(a.warmup, 2))
+        vps, cores, sample, ms = cpu_reference_run(a, steps, warmup, a.cpu_budget_s)
+        line = {"impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": a.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(a), "points": a.points, "resolution": a.res,
+                           "views_per_step_per_gpu": a.views, "sh_degree": a.sh_degree},
+                "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "the reference's rasterizer is an external CUDA-only dependency absent from the tree; "
+                        "this arm is the CPU oracle port of its published algorithm (oracle/splat_torch.py)"}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gaussianip_b200 has no CPU fallback")
+    import torch.distributed as dist
+    from gaussianip_b200 import _lib, multiview, rasterizer, renderer, synthetic
+    from gaussianip_b200.cameras import Camera, look_at_c2w, orbit_position
+    import numpy as np
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    # ---- workload: shared cloud (same on all ranks), per-rank cameras and loss weights ----
+    cloud_host = synthetic.make_cloud(a.points, a.sh_degree, 0)
+    host = {k: getattr(cloud_host, k).pin_memory() for k in
+            ("xyz", "features_dc", "features_rest", "scaling", "rotation", "opacity")}
+    params = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
+
+    class Model:            # GaussianModel getters (gaussian_model.py:84-107) over a dict of leaves
+        active_sh_degree = a.sh_degree
+
+        def __init__(self, p):
+            self.p = p
+        get_xyz = property(lambda s: s.p["xyz"])
+        get_features = property(lambda s: torch.cat((s.p["features_dc"], s.p["features_rest"]), dim=1))
+        get_opacity = property(lambda s: torch.sigmoid(s.p["opacity"]))
+        get_scaling = property(lambda s: torch.exp(s.p["scaling"]))
+        get_rotation = property(lambda s: torch.nn.functional.normalize(s.p["rotation"]))
+
+    rng = np.random.default_rng(1000 + rank)
+
+    def sample_cameras_host():
+        """camera_data.py:349-364 distributions; returns (c2w, fovy) per view, host side."""
+        out = []
+        for i in range(a.views):
+            az = (rng.random() + i) / a.views * 360.0 - 180.0
+            out.append((look_at_c2w(orbit_position(az, rng.uniform(-30, 30), rng.uniform(1.3, 1.7))),
+                        float(np.radians(rng.uniform(40, 70)))))
+        return out
+
+    total_steps = a.warmup + a.steps
+    cam_specs = [sample_cameras_host() for _ in range(total_steps)]
+    gen = torch.Generator().manual_seed(2 + rank)
+    weights = [tuple(torch.randn(c, a.res, a.res, generator=gen).to(dev) for c in (3, 1, 1)) for _ in range(a.views)]
+    bg = torch.zeros(3, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    vp = multiview.ViewParallel(params, a.points)
+    model = Model(params)
+
+    def loss_of(v, out):
+        w = weights[v]
+        return (out["render"] * w[0]).sum() + (out["depth_3dgs"] * w[1]).sum() + (out["alpha_3dgs"] * w[2]).sum()
+
+    def run_step(step_idx, cams):
+        def render_fn(v, vsp):
+            return renderer.render(cams[v], model, None, bg, screenspace_points=vsp)
+        return vp.step(a.views, render_fn, loss_of, views=range(a.views))
+
+    def device_cams(step_idx):
+        return [Camera(c2w, fovy, a.res, a.res, data_device=dev) for c2w, fovy in cam_specs[step_idx]]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: inputs resident in HBM ------------------------------------------------------
+    cams_all = [device_cams(i) for i in range(total_steps)]
+    for i in range(a.warmup):
+        run_step(i, cams_all[i])
+    barrier()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    d_sum = 0
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(a.steps):
+        flush_buf.fill_(k & 0xFF)               # L2 flush between timed steps (outside the event pair)
+        ev[k][0].record()
+        run_step(a.warmup + k, cams_all[a.warmup + k])
+        ev[k][1].record()
+        d_sum += rasterizer._workspace(dev).last_num_rendered
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clock_info = clocks.stop() if rank == 0 else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    my_ms = sum(step_ms)
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    views_total = a.views * world * a.steps
+    value = views_total / (total_ms * 1e-3)
+
+    # ---- leg 2: end to end from pinned host buffers -----------------------------------------
+    def e2e_step(step_idx):
+        for k2, h in host.items():          # H2D of every parameter tensor of the step
+            params[k2].data.copy_(h, non_blocking=True)
+        cams = device_cams(step_idx)        # camera matrices built on host, uploaded per view
+        out = run_step(step_idx, cams)
+        return float(out["loss"].item())    # D2H read of the step's result
+
+    for i in range(min(3, a.warmup)):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(a.steps):
+        e2e_step(a.warmup + k)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = views_total / (float(t2.item()) * 1e-3)
+    h2d = sum(h.numel() * 4 for h in host.values()) + a.views * (16 + 16 + 16 + 3) * 4
+    d2h = 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    D = d_sum / max(1, a.steps)              # D of the last view of each step, averaged
+    HW, P, K = a.res * a.res, a.points, (a.sh_degree + 1) ** 2
+    alg_bytes = {   # SURVEY.md §8(d) per-stage algorithmic bytes
+        "preprocess_fwd": P * (44 + 12 * K + 48), "depth_sort": 4 * 16 * P, "scan_emit": 8 * P + 20 * P + 12 * D,
+        "tile_sort": 2 * 16 * D, "ranges": 8 * D, "render_fwd": 44 * D + 28 * HW,
+        "render_bwd": 44 * D + 28 * HW + 40 * P, "preprocess_bwd": P * (40 + 44 + 12 * K + 56 + 12 * K)}
+    stage_ms = {k: (m / c if c else 0.0) for k, (m, c) in prof.items()}
+    dom = max(stage_ms, key=lambda k: stage_ms[k] * prof[k][1])
+    achieved = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    b_view = P * (300 + 36 * K) + 260 * D + 56 * HW
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dom], "avg_launch_ms": stage_ms[dom],
+                "whole_view": {"algorithmic_bytes": b_view, "achieved_gbs": b_view * value / world / 1e9,
+                               "frac": b_view * value / world / 1e9 / peak},
+                "secondary": {"bound": "alu/mufu", "pair_evals_upper_bound_per_s": 256 * D / (stage_ms[dom] * 1e-3)
+                              if stage_ms[dom] > 0 else None},
+                "stage_us_per_view": {k: round(v * 1e3, 1) for k, v in stage_ms.items()}}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        vps, cores, sample, _ = cpu_reference_run(a, 1, 0, 40.0)
+        cpu = {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "points": a.points, "resolution": a.res,
+                       "views_per_step_per_gpu": a.views, "sh_degree": a.sh_degree, "num_rendered_D": D,
+                       "l2": "256 MiB flush write between timed steps (outside the event pairs)",
+                       "parallelism": f"view-sharded dp{world}, NCCL all-reduce of the flat gradient bucket "
+                                      f"({vp.bucket.nbytes() >> 20} MiB) + radii max per step" if world > 1 else "single GPU",
+                       "wall_s_timed_region": t_wall},
+            "clocks": clock_info,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

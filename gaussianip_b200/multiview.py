@@ -1,0 +1,136 @@
+"""View-sharded data parallelism over the B200s of one box.
+
+The path shards by CAMERA VIEW: every rank holds a full replica of the Gaussian parameters,
+view ``v`` of a step goes to rank ``v mod world`` (the reference simply loops over the views
+on one GPU: threestudio/systems/GaussianIP.py:154-159, 305-307).  There is exactly one
+exchange step per optimiser step:
+
+1. ``all_reduce(SUM)`` of ONE flat fp32 bucket that holds every parameter gradient AND the
+   summed screen-space gradient (the reference sums ``viewspace_points.grad`` over views
+   BEFORE taking the norm, GaussianIP.py:450-457, so the sum is what must be reduced);
+   autograd accumulates straight into views of that bucket, so nothing is packed or copied
+   before NCCL;
+2. ``all_reduce(MAX)`` of ``radii`` (-> visibility_filter, max_radii2D; GaussianIP.py:161-167, 456).
+
+Afterwards the densification statistics (gaussian_model.py:420-422) are updated identically
+on every rank, so replicas stay bit-identical without further traffic.
+
+Nothing in this module touches CUDA directly: it works on whatever device the tensors live
+on, which is how the world_size-2 ``gloo`` tests exercise it on CPU.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Interleaved assignment v -> v mod world (neighbouring azimuths differ little in cost,
+    so interleaving balances front / side views across ranks)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_views, world))
+
+
+class GradBucket:
+    """One flat fp32 buffer; named views are installed as ``.grad`` of the leaf parameters."""
+
+    VIEWSPACE = "__viewspace__"
+
+    def __init__(self, params: Dict[str, torch.Tensor], n_points: int):
+        if not params:
+            raise ValueError("no parameters")
+        first = next(iter(params.values()))
+        self.device = first.device
+        self.names = list(params) + [self.VIEWSPACE]
+        shapes = {k: tuple(v.shape) for k, v in params.items()}
+        shapes[self.VIEWSPACE] = (n_points, 3)
+        self.shapes = shapes
+        sizes = [int(torch.Size(shapes[k]).numel()) for k in self.names]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        self.flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=self.device)
+        self.views = {k: self.flat[self.offsets[i]:self.offsets[i + 1]].view(shapes[k])
+                      for i, k in enumerate(self.names)}
+        self.params = params
+        # shared zero-valued carrier for the screen-space gradient of every local view
+        self.viewspace_points = torch.zeros(n_points, 3, dtype=torch.float32, device=self.device,
+                                            requires_grad=True)
+
+    def attach(self) -> None:
+        """Point every leaf's .grad at its bucket view (autograd then accumulates in place)."""
+        for k, p in self.params.items():
+            if p.dtype != torch.float32:
+                raise ValueError(f"{k}: bucket holds fp32 gradients only")
+            p.grad = self.views[k]
+        self.viewspace_points.grad = self.views[self.VIEWSPACE]
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def all_reduce(self, group=None, async_op: bool = False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return None
+
+    def viewspace_grad(self) -> torch.Tensor:
+        return self.views[self.VIEWSPACE]
+
+
+def all_reduce_radii_max(radii: torch.Tensor, group=None) -> torch.Tensor:
+    """radii: per-rank max over local views, int32 [P]; reduced in place."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(radii, op=dist.ReduceOp.MAX, group=group)
+    return radii
+
+
+def add_densification_stats(xyz_gradient_accum: torch.Tensor, denom: torch.Tensor, max_radii2D: torch.Tensor,
+                            viewspace_grad: torch.Tensor, radii: torch.Tensor) -> torch.Tensor:
+    """GaussianIP.py:456-457 + gaussian_model.py:420-422 on the REDUCED quantities.  Returns the
+    visibility filter.  Mask-multiply form (no boolean indexing -> no device sync)."""
+    vis = radii > 0
+    m = vis.to(xyz_gradient_accum.dtype)
+    xyz_gradient_accum.add_((torch.norm(viewspace_grad[:, :2], dim=-1, keepdim=True)) * m[:, None])
+    denom.add_(m[:, None])
+    torch.maximum(max_radii2D, torch.where(vis, radii.to(max_radii2D.dtype), max_radii2D), out=max_radii2D)
+    return vis
+
+
+class ViewParallel:
+    """Runs one optimisation step's worth of views, sharded over the process group.
+
+    render_fn(view_index, viewspace_points) -> dict with at least 'radii' and whatever loss_fn
+    needs; loss_fn(view_index, render_dict) -> scalar loss of that view.
+    """
+
+    def __init__(self, params: Dict[str, torch.Tensor], n_points: int, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket = GradBucket(params, n_points)
+        self.n_points = n_points
+
+    def step(self, n_views: int, render_fn: Callable, loss_fn: Callable, views: Optional[Sequence[int]] = None):
+        b = self.bucket
+        b.zero_()
+        b.attach()
+        local = shard_views(n_views, self.rank, self.world) if views is None else list(views)
+        radii = torch.zeros(self.n_points, dtype=torch.int32, device=b.device)
+        total = torch.zeros((), dtype=torch.float32, device=b.device)
+        for v in local:
+            out = render_fn(v, b.viewspace_points)
+            radii = torch.maximum(radii, out["radii"])
+            loss = loss_fn(v, out)
+            loss.backward()            # accumulates into the bucket views, view after view
+            total = total + loss.detach()
+        b.all_reduce(self.group)
+        all_reduce_radii_max(radii, self.group)
+        if self.world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return {"loss": total, "radii": radii, "viewspace_grad": b.viewspace_grad(), "local_views": local}

@@ -51,13 +51,18 @@ def _settings(cam, bg_color, scaling_modifier, sh_degree):
         prefiltered=False, debug=False)
 
 
-def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+           screenspace_points=None):
+    """``screenspace_points`` (additive, optional): a caller-owned zero-valued [P,3] leaf to use as
+    the screen-space gradient carrier instead of a fresh tensor per view, so the per-view
+    gradients sum in place (gaussianip_b200.multiview.GradBucket)."""
     xyz = _get(pc, "get_xyz")
-    screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    if screenspace_points is None:
+        screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
     sh_degree = getattr(pc, "active_sh_degree", getattr(pc, "sh_degree", 0))
     rasterizer = GaussianRasterizer(_settings(viewpoint_camera, bg_color, scaling_modifier, sh_degree))
     scales = rotations = cov3D_precomp = None

@@ -347,8 +347,10 @@ class Image:
 
 
 def blend_tiles(g: Geom, b: Binning, bg: torch.Tensor, H: int, W: int, chunk: int = 2048,
-                margin: float = 2e-5) -> Image:
-    """Per-tile front-to-back alpha blend (Appendix A, 'Forward blend'), differentiable."""
+                margin: float = 2e-5, tile_rows=None) -> Image:
+    """Per-tile front-to-back alpha blend (Appendix A, 'Forward blend'), differentiable.
+    tile_rows=(phase, stride) blends only tile rows r with r % stride == phase (a bounded
+    sample for CPU timing); the other tiles keep the background."""
     dt = g.xy.dtype
     gx, gy = b.grid
     color = torch.zeros(3, gy * BLOCK_Y, gx * BLOCK_X, dtype=dt)
@@ -367,6 +369,8 @@ def blend_tiles(g: Geom, b: Binning, bg: torch.Tensor, H: int, W: int, chunk: in
         if e <= s:
             continue
         ty_, tx_ = divmod(t, gx)
+        if tile_rows is not None and ty_ % tile_rows[1] != tile_rows[0]:
+            continue
         pxf = (tx_ * BLOCK_X + lx).to(dt)
         pyf = (ty_ * BLOCK_Y + ly).to(dt)
         Tcur = torch.ones(256, dtype=dt)
@@ -442,7 +446,7 @@ def blend_tiles(g: Geom, b: Binning, bg: torch.Tensor, H: int, W: int, chunk: in
 
 
 def rasterize(settings: Settings, means3D, means2D, opacities, shs=None, colors_precomp=None,
-              scales=None, rotations=None, cov3D_precomp=None, return_aux: bool = False):
+              scales=None, rotations=None, cov3D_precomp=None, return_aux: bool = False, tile_rows=None):
     """The operator: same argument meaning and return tuple as
     GaussianRasterizer.forward (called at gaussian_renderer/__init__.py:85-93)."""
     if (shs is None) == (colors_precomp is None):
@@ -454,7 +458,7 @@ def rasterize(settings: Settings, means3D, means2D, opacities, shs=None, colors_
     g = preprocess(settings, means3D, opacities, shs, colors_precomp, scales, rotations,
                    cov3D_precomp, means2D)
     b = bin_and_sort(g, H, W)
-    img = blend_tiles(g, b, settings.bg, H, W)
+    img = blend_tiles(g, b, settings.bg, H, W, tile_rows=tile_rows)
     if return_aux:
         return img.color, g.radii, img.depth, img.alpha, g, b, img
     return img.color, g.radii, img.depth, img.alpha
