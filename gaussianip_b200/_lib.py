@@ -21,7 +21,7 @@ class GsbSettings(C.Structure):
 
 
 _LAYOUT_FIELDS = ["saved_bytes", "off_geom", "off_clamped", "off_counts", "off_point_list", "off_ranges",
-                  "off_n_contrib", "off_final_T", "scratch_bytes", "off_rect", "off_tiles", "off_dkeys0",
+                  "off_n_contrib", "off_final_T", "off_tile_order", "scratch_bytes", "off_rect", "off_tiles", "off_dkeys0",
                   "off_dkeys1", "off_dkeys2", "off_didx0", "off_didx1", "off_offsets", "off_blocksums",
                   "off_hist", "off_tkeys0", "off_tkeys1", "off_tvals_alt", "off_keys64_0", "off_keys64_1",
                   "off_ggrad"]

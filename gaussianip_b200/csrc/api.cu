@@ -79,6 +79,7 @@ static int layout(int P, int H, int W, long long D_cap, GsbLayout* L) {
   L->off_ranges = take(T * sizeof(uint2));
   L->off_n_contrib = take(HW * 4);
   L->off_final_T = take(HW * 4);
+  L->off_tile_order = take(T * 4);
   L->saved_bytes = o;
   o = 0;
   L->off_rect = take(Pz * 8);
@@ -193,7 +194,8 @@ int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap, fl
   if (rc) return rc;
   ProfScope ps(GSB_STAGE_RENDER_FWD, (cudaStream_t)stream);
   return launch_render_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
-                           at<uint2>(saved, L.off_ranges), out_color, out_depth, out_alpha,
+                           at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order), out_color,
+                           out_depth, out_alpha,
                            at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
                            (cudaStream_t)stream);
 }
@@ -231,8 +233,8 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
   if (rc) return rc;
   ProfScope ps(GSB_STAGE_RENDER_BWD, (cudaStream_t)stream);
   return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
-                           at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_n_contrib),
-                           at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
+                           at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order),
+                           at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
                            at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
 }
 

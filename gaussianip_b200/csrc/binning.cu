@@ -278,6 +278,29 @@ __global__ void tile_ranges_kernel(const KeyT* __restrict__ keys, const uint32_t
   if (i == n - 1) ranges[t].y = (uint32_t)n;
 }
 
+// Heaviest-first CTA order for the blend kernels: tiles bucketed by floor(log2(list length)),
+// longest bucket first (order inside a bucket is irrelevant: it only affects scheduling).
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(const uint2* __restrict__ ranges, int T, uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_cnt[33], s_cur[33];
+  if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    atomicAdd(&s_cnt[32 - __clz(r.y - r.x)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int b = 32; b >= 0; --b) { s_cur[b] = run; run += s_cnt[b]; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    order[atomicAdd(&s_cur[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)t;
+  }
+}
+
 __global__ void compose_keys_kernel(const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ point_list,
                                     const uint32_t* __restrict__ dkeys, const uint32_t* __restrict__ d_n,
                                     long long n_cap, uint64_t* __restrict__ out) {
@@ -362,6 +385,8 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   };
   if (P == 0) {
     GSB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(uint32_t), st));
+    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order));
+    GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
     return publish();
   }
   const int sc_blocks = (P + SC_TILE - 1) / SC_TILE;
@@ -407,6 +432,8 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     // (a single-tile image needs 0 passes: the emitted order in B is already final)
     tile_ranges_kernel<uint32_t><<<cap_blocks, 256, 0, st>>>(inA ? tkA : tkB, counts + CNT_D, D_cap, ranges);
     GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
+    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order));
+    GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
     return GSB_OK;
   }
   if (mode == GSB_BIN_FLAT64) {
@@ -434,6 +461,8 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     ProfScope pr(GSB_STAGE_RANGES, st);
     tile_ranges_kernel<uint64_t><<<cap_blocks, 256, 0, st>>>(inA ? kA : kB, counts + CNT_D, D_cap, ranges);
     GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
+    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order));
+    GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
     return GSB_OK;
   }
   return GSB_E_INVALID;

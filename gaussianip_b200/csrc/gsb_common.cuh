@@ -17,16 +17,19 @@ constexpr float T_MIN = 0.0001f;
 
 // Per-Gaussian record gathered by the blend kernels: 48 B, 16 B aligned, three float4.
 struct __align__(16) Geom {
-  float x, y, ca, cb;         // pixel centre, conic A, conic B
-  float cc, opacity, depth, r;  // conic C, opacity, view z, red
-  float g, b, extx, exty;     // green, blue, conservative half-extent of {alpha >= 1/255} in px
+  float x, y, extx, exty;       // pixel centre, conservative half-extent of {alpha >= 1/255} in px
+  float ca, cb, cc, opacity;    // conic A, B, C, opacity
+  float depth, r, g, b;         // view z, colour
 };
 static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
 
 // Per-Gaussian gradient record accumulated by render_bwd (atomics land in one 48 B span).
+// With s = dL/dG * G per (pixel, Gaussian) and d = centre - pixel, the first five slots are the
+// raw moments sum(s dx), sum(s dy), sum(s dx^2), sum(s dx dy), sum(s dy^2); preprocess_bwd maps
+// them to dL/d(ndc xy) and dL/d(conic).
 struct __align__(16) GGrad {
-  float dx, dy, dA, dB;       // dL/d(ndc xy), dL/dconic A, B
-  float dC, dop, ddepth, dr;  // dL/dconic C, dL/dopacity, dL/ddepth, dL/dred
+  float sx, sy, sxx, sxy;
+  float syy, dop, ddepth, dr;  // ..., dL/dopacity, dL/ddepth, dL/dred
   float dg, db, pad0, pad1;
 };
 static_assert(sizeof(GGrad) == 48, "GGrad must be 48 bytes");
@@ -99,12 +102,12 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
                     cudaStream_t st);
 
 int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
-                      const uint2* ranges, float* color, float* depth, float* alpha,
+                      const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
                       uint32_t* n_contrib, float* final_T, bool debug, cudaStream_t st);
 
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
-                      const uint2* ranges, const uint32_t* n_contrib, const float* final_T,
-                      const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                      const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
+                      const float* final_T, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                       GGrad* ggrad, bool debug, cudaStream_t st);
 
 int launch_preprocess_bwd(const View& v, int P, int K, const float* means3D, const float* scales,

@@ -169,14 +169,10 @@ preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
           ex = sqrtf(2.0f * tau * a) * 1.002f + 0.05f;
           ey = sqrtf(2.0f * tau * c) * 1.002f + 0.05f;
         }
-        Geom rec;
-        rec.x = pixx; rec.y = pixy; rec.ca = cA; rec.cb = cB;
-        rec.cc = cC; rec.opacity = o; rec.depth = tz; rec.r = r_;
-        rec.g = g_; rec.b = b_; rec.extx = ex; rec.exty = ey;
         float4* dst = reinterpret_cast<float4*>(geom + i);
-        dst[0] = make_float4(rec.x, rec.y, rec.ca, rec.cb);
-        dst[1] = make_float4(rec.cc, rec.opacity, rec.depth, rec.r);
-        dst[2] = make_float4(rec.g, rec.b, rec.extx, rec.exty);
+        dst[0] = make_float4(pixx, pixy, ex, ey);
+        dst[1] = make_float4(cA, cB, cC, o);
+        dst[2] = make_float4(tz, r_, g_, b_);
         clamped[i] = cl;
         rect[i] = make_ushort4((unsigned short)minx, (unsigned short)miny, (unsigned short)maxx,
                                (unsigned short)maxy);

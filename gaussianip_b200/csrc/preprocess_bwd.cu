@@ -18,8 +18,8 @@ __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rots,
                       const float* __restrict__ shs, const float* __restrict__ cov3Dp,
-                      const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
-                      const GGrad* __restrict__ ggrad, float* __restrict__ dmeans3D,
+                      const int32_t* __restrict__ radii, const Geom* __restrict__ geom,
+                      const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, float* __restrict__ dmeans3D,
                       float* __restrict__ dmeans2D, float* __restrict__ dshs, float* __restrict__ dcolors,
                       float* __restrict__ dopac, float* __restrict__ dscales, float* __restrict__ drots,
                       float* __restrict__ dcov3D, int acc) {
@@ -47,7 +47,11 @@ preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
 
   const float4* gp = reinterpret_cast<const float4*>(ggrad + i);
   const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
-  const float gx = g0.x, gy = g0.y, gA = g0.z, gB = g0.w, gC = g1.x, gop = g1.y, gdepth = g1.z;
+  // moments -> gradients of the screen-space mean (NDC units) and of the conic
+  const float4 con = reinterpret_cast<const float4*>(geom + i)[1];   // conA, conB, conC, opacity
+  const float gx = -(con.x * g0.x + con.y * g0.y) * (0.5f * (float)v.W);
+  const float gy = -(con.z * g0.y + con.y * g0.x) * (0.5f * (float)v.H);
+  const float gA = -0.5f * g0.z, gB = -g0.w, gC = -0.5f * g1.x, gop = g1.y, gdepth = g1.z;
   float grgb[3] = {g1.w, g2.x, g2.y};
 
   const float px = means3D[3 * i], py = means3D[3 * i + 1], pz = means3D[3 * i + 2];
@@ -280,10 +284,10 @@ int launch_preprocess_bwd(const View& v, int P, int K, const float* means3D, con
                           float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors,
                           float* dopac, float* dscales, float* drots, float* dcov3D,
                           int accumulate, bool debug, cudaStream_t st) {
-  (void)opac; (void)geom; (void)colors;
+  (void)opac; (void)colors;
   if (P == 0) return GSB_OK;
   preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(v, P, K, means3D, scales, rots, shs, cov3D, radii,
-                                                         clamped, ggrad, dmeans3D, dmeans2D, dshs, dcolors,
+                                                         geom, clamped, ggrad, dmeans3D, dmeans2D, dshs, dcolors,
                                                          dopac, dscales, drots, dcov3D, accumulate);
   GSB_POST_LAUNCH(debug, st, "preprocess_bwd_kernel");
   return GSB_OK;

@@ -1,10 +1,11 @@
 // Backward stage 1: per-pixel reverse (back-to-front) blending.  Replaces renderCUDA
 // (backward) of the external operator ("Backward blend").
 //
-// Same tiling as render_fwd.cu (one CTA per 16x16 tile, warp = 8x4 pixels, cp.async
-// double-buffered gathers, per-warp conservative culling).  Differences that matter:
-//  * the walk starts at the LAST instance any pixel of the tile actually blended
-//    (block max of n_contrib), not at the end of the tile's list;
+// Same organisation as render_fwd.cu: one CTA per 16x16 tile, warp = 8x4 pixels, warps fully
+// independent (no __syncthreads), per-warp cp.async ring of 32-instance chunks, per-warp
+// conservative culling.  Differences that matter:
+//  * each warp starts at the LAST instance any of ITS pixels blended (warp max of n_contrib),
+//    not at the end of the tile's list, and walks towards the front;
 //  * the ten per-Gaussian partial gradients of the 32 pixels of a warp are summed with a
 //    13-shuffle multi-value butterfly and leave the SM as ONE red.global per component per
 //    (warp, Gaussian) — 10 lanes hitting one 48 B GGrad record — instead of ~10 atomicAdd
@@ -15,11 +16,15 @@ namespace gsb {
 
 namespace {
 
-constexpr int BATCH = 256;
+constexpr int WARPS = 8;
+#ifndef GSB_BWD_STAGES
+#define GSB_BWD_STAGES 4
+#endif
+constexpr int STAGES = GSB_BWD_STAGES;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -59,21 +64,21 @@ __device__ __forceinline__ float butterfly12(const float (&v)[12], int lane) {
   return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(WARPS * 32)
 render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
-                  const uint2* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
-                  const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
+                  const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                  const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
+                  const float* __restrict__ dL_dcolor,
                   const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
                   GGrad* __restrict__ ggrad) {
-  __shared__ float4 s_a[2][BATCH];
-  __shared__ float4 s_b[2][BATCH];
-  __shared__ float4 s_c[2][BATCH];
-  __shared__ uint32_t s_gid[2][BATCH];
-  __shared__ uint32_t s_max[8];
+  extern __shared__ float4 smem_dyn[];
+  float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
+  uint32_t (*s_gid)[STAGES][32] =
+      reinterpret_cast<uint32_t (*)[STAGES][32]>(smem_dyn + WARPS * STAGES * 3 * 32);
 
-  const int tile = blockIdx.x;
+  const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
   const int pix_x = tx * TILE_X + wx + (lane & 7);
   const int pix_y = ty * TILE_Y + wy + (lane >> 3);
@@ -85,15 +90,10 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 
   const uint2 range = ranges[tile];
   const uint32_t my_last = inside ? n_contrib[pix] : 0u;
-  const uint32_t warp_last = __reduce_max_sync(0xffffffffu, my_last);
-  if (lane == 0) s_max[warp] = warp_last;
-  __syncthreads();
-  uint32_t n_eff = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) n_eff = max(n_eff, s_max[w]);
-  if (n_eff == 0) return;
-  const int n = (int)n_eff;  // <= range.y - range.x
-  const int rounds = (n + BATCH - 1) / BATCH;
+  const int n = (int)__reduce_max_sync(0xffffffffu, my_last);   // instances this warp must revisit
+  if (n == 0) return;
+  const int chunks = (n + 31) >> 5;
+  const uint32_t* pl = point_list + range.x;
 
   const float T_final = inside ? final_T[pix] : 0.0f;
   float T = T_final;
@@ -103,126 +103,152 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   const float bg_dot = v.bg[0] * gC0 + v.bg[1] * gC1 + v.bg[2] * gC2;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
   float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lD = 0.f;
-  const float half_W = 0.5f * (float)v.W, half_H = 0.5f * (float)v.H;
 
-  auto issue = [&](int b, uint32_t gid) {
-    const int e = b * BATCH + tid;
-    if (e < n) {
-      const float4* src = reinterpret_cast<const float4*>(geom + gid);
-      const int buf = b & 1;
-      cp_async16(&s_a[buf][tid], src);
-      cp_async16(&s_b[buf][tid], src + 1);
-      cp_async16(&s_c[buf][tid], src + 2);
-      s_gid[buf][tid] = gid;
+  float4 (*ring)[3][32] = s_rec[warp];
+  uint32_t (*gring)[32] = s_gid[warp];
+  // chunk index c counts from the BACK: it covers list positions [(chunks-1-c)*32, +32)
+  auto issue = [&](int c, uint32_t gid) {
+    if (c < chunks) {
+      const int e = (chunks - 1 - c) * 32 + lane;
+      if (e < n) {
+        const float4* src = reinterpret_cast<const float4*>(geom + gid);
+        float4 (*st)[32] = ring[c & (STAGES - 1)];
+        cp_async16(&st[0][lane], src);
+        cp_async16(&st[1][lane], src + 1);
+        cp_async16(&st[2][lane], src + 2);
+        gring[c & (STAGES - 1)][lane] = gid;
+      }
     }
     cp_async_commit();
   };
-  auto fetch_gid = [&](int b) -> uint32_t {
-    const int e = b * BATCH + tid;
-    return (b >= 0 && e < n) ? point_list[range.x + e] : 0u;
+  auto fetch_gid = [&](int c) -> uint32_t {
+    if (c >= chunks) return 0u;
+    const int e = (chunks - 1 - c) * 32 + lane;
+    return e < n ? pl[e] : 0u;
   };
-
-  issue(rounds - 1, fetch_gid(rounds - 1));
-  uint32_t gid_next = fetch_gid(rounds - 2);
-  for (int b = rounds - 1; b >= 0; --b) {
-    if (b > 0) {
-      issue(b - 1, gid_next);
-      gid_next = fetch_gid(b - 2);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const int buf = b & 1;
-    const int cnt = min(BATCH, n - b * BATCH);
-    if ((uint32_t)(b * BATCH) < warp_last) {
-      for (int j = (cnt - 1) / 32; j >= 0; --j) {
-        if ((uint32_t)(b * BATCH + j * 32) >= warp_last) continue;
-        const int e = j * 32 + lane;
-        bool hit = false;
-        if (e < cnt) {
-          const float4 a = s_a[buf][e];
-          const float4 c = s_c[buf][e];
-          hit = (fabsf(a.x - cxw) <= c.z + 3.5f) && (fabsf(a.y - cyw) <= c.w + 1.5f);
-        }
-        uint32_t mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-          const int k = 31 - __clz(mask);
-          mask &= ~(1u << k);
-          const int e2 = j * 32 + k;
-          const uint32_t pos = (uint32_t)(b * BATCH + e2 + 1);
-          const float4 a = s_a[buf][e2];
-          const float4 q = s_b[buf][e2];
-          const float4 c = s_c[buf][e2];
-          float g[12];
 #pragma unroll
-          for (int i = 0; i < 12; ++i) g[i] = 0.0f;
-          bool contributes = false;
-          if (pos <= my_last) {
-            const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = -0.5f * (a.z * dx * dx + q.x * dy * dy) - a.w * dx * dy;
-            if (power <= 0.0f) {
-              const float G = __expf(power);
-              const float alpha = fminf(ALPHA_CAP, q.y * G);
-              if (alpha >= ALPHA_MIN) {
-                contributes = true;
-                T = T / (1.0f - alpha);
-                const float w = alpha * T;
-                float dL_da = 0.0f;
-                acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0; lc0 = q.w;
-                acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1; lc1 = c.x;
-                acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2; lc2 = c.y;
-                accD = last_alpha * lD + (1.0f - last_alpha) * accD; lD = q.z;
-                accA = last_alpha + (1.0f - last_alpha) * accA;
-                dL_da += (q.w - acc0) * gC0 + (c.x - acc1) * gC1 + (c.y - acc2) * gC2;
-                dL_da += (q.z - accD) * gD;
-                dL_da += (1.0f - accA) * gA;
-                dL_da *= T;
-                last_alpha = alpha;
-                dL_da += (-T_final / (1.0f - alpha)) * bg_dot;
-                const float dL_dG = q.y * dL_da;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_dx = -gdx * a.z - gdy * a.w;
-                const float dG_dy = -gdy * q.x - gdx * a.w;
-                g[0] = dL_dG * dG_dx * half_W;
-                g[1] = dL_dG * dG_dy * half_H;
-                g[2] = -0.5f * gdx * dx * dL_dG;
-                g[3] = -gdx * dy * dL_dG;
-                g[4] = -0.5f * gdy * dy * dL_dG;
-                g[5] = G * dL_da;
-                g[6] = w * gD;
-                g[7] = w * gC0;
-                g[8] = w * gC1;
-                g[9] = w * gC2;
-              }
-            }
-          }
-          if (!__any_sync(0xffffffffu, contributes)) continue;
-          const float total = butterfly12(g, lane);
-          const int slot = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-          const bool pad = (lane & 4) && (lane & 2);
-          if (!(lane & 1) && !pad && slot < 10 && total != 0.0f) {
-            float* dst = reinterpret_cast<float*>(ggrad + s_gid[buf][e2]) + slot;
-            atomicAdd(dst, total);
-          }
+  for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_gid(c));
+  uint32_t gid_next = fetch_gid(STAGES - 1);
+
+  for (int c = 0; c < chunks; ++c) {
+    issue(c + STAGES - 1, gid_next);
+    gid_next = fetch_gid(c + STAGES);
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    float4 (*st)[32] = ring[c & (STAGES - 1)];
+    const int base = (chunks - 1 - c) * 32;
+    const int e = base + lane;
+    bool hit = false;
+    if (e < n) {
+      const float4 a = st[0][lane];
+      hit = (fabsf(a.x - cxw) <= a.z + 3.5f) && (fabsf(a.y - cyw) <= a.w + 1.5f);
+    }
+    uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    // Hits are taken two at a time (back to front): the geometry/alpha of both are independent
+    // and the two 13-shuffle reductions interleave, hiding most of their latency chains.
+    while (mask) {
+      int k[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        k[i] = mask ? 31 - __clz(mask) : -1;
+        if (k[i] >= 0) mask &= ~(1u << k[i]);
+      }
+      float dx[2], dy[2], G[2], alpha[2];
+      float4 q[2], f[2];
+      bool valid[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        valid[i] = false;
+        if (k[i] >= 0) {
+          const float4 a = st[0][k[i]];
+          q[i] = st[1][k[i]];
+          f[i] = st[2][k[i]];
+          dx[i] = a.x - pxf; dy[i] = a.y - pyf;
+          const float power = -0.5f * (q[i].x * dx[i] * dx[i] + q[i].z * dy[i] * dy[i]) - q[i].y * dx[i] * dy[i];
+          G[i] = __expf(power);
+          alpha[i] = fminf(ALPHA_CAP, q[i].w * G[i]);
+          valid[i] = ((uint32_t)(base + k[i] + 1) <= my_last) && power <= 0.0f && alpha[i] >= ALPHA_MIN;
         }
       }
+      float g[2][12];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) g[i][j] = 0.0f;
+        if (valid[i]) {
+          const float inv1ma = __fdividef(1.0f, 1.0f - alpha[i]);
+          T *= inv1ma;
+          const float w = alpha[i] * T;
+          acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0; lc0 = f[i].y;
+          acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1; lc1 = f[i].z;
+          acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2; lc2 = f[i].w;
+          accD = last_alpha * lD + (1.0f - last_alpha) * accD; lD = f[i].x;
+          accA = last_alpha + (1.0f - last_alpha) * accA;
+          float dL_da = (f[i].y - acc0) * gC0 + (f[i].z - acc1) * gC1 + (f[i].w - acc2) * gC2;
+          dL_da += (f[i].x - accD) * gD;
+          dL_da += (1.0f - accA) * gA;
+          dL_da *= T;
+          last_alpha = alpha[i];
+          dL_da -= T_final * inv1ma * bg_dot;
+          // raw moments of s = dL/dG * G about the splat centre; the linear maps to
+          // d(ndc xy) and d(conic) are applied once per Gaussian in preprocess_bwd
+          const float s_ = q[i].w * dL_da * G[i];
+          g[i][0] = s_ * dx[i];
+          g[i][1] = s_ * dy[i];
+          g[i][2] = g[i][0] * dx[i];
+          g[i][3] = g[i][0] * dy[i];
+          g[i][4] = g[i][1] * dy[i];
+          g[i][5] = G[i] * dL_da;
+          g[i][6] = w * gD;
+          g[i][7] = w * gC0;
+          g[i][8] = w * gC1;
+          g[i][9] = w * gC2;
+        }
+      }
+      const bool any0 = __any_sync(0xffffffffu, valid[0]);
+      const bool any1 = __any_sync(0xffffffffu, valid[1]);
+      const int slot = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+      const bool writer = !(lane & 1) && !((lane & 4) && (lane & 2)) && slot < 10;
+      float tot0 = 0.0f, tot1 = 0.0f;
+      if (any0 && any1) {
+        tot0 = butterfly12(g[0], lane);
+        tot1 = butterfly12(g[1], lane);
+      } else if (any0) {
+        tot0 = butterfly12(g[0], lane);
+      } else if (any1) {
+        tot1 = butterfly12(g[1], lane);
+      }
+      if (writer) {
+        if (any0 && tot0 != 0.0f)
+          atomicAdd(reinterpret_cast<float*>(ggrad + gring[c & (STAGES - 1)][k[0]]) + slot, tot0);
+        if (any1 && tot1 != 0.0f)
+          atomicAdd(reinterpret_cast<float*>(ggrad + gring[c & (STAGES - 1)][k[1]]) + slot, tot1);
+      }
     }
-    __syncthreads();
+    __syncwarp();
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace
 
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
-                      const uint2* ranges, const uint32_t* n_contrib, const float* final_T,
-                      const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                      GGrad* ggrad, bool debug, cudaStream_t st) {
+                      const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
+                      const float* final_T, const float* dL_dcolor, const float* dL_ddepth,
+                      const float* dL_dalpha, GGrad* ggrad, bool debug, cudaStream_t st) {
   GSB_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)P * sizeof(GGrad), st));
   const int T = v.gx * v.gy;
   if (T == 0 || P == 0) return GSB_OK;
-  render_bwd_kernel<<<T, 256, 0, st>>>(v, geom, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth,
-                                       dL_dalpha, ggrad);
+  constexpr size_t smem = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
+  static bool configured[64] = {};   // the attribute is per device
+  int dev = 0;
+  GSB_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev & 63] = true;
+  }
+  render_bwd_kernel<<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
+                                              dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
   GSB_POST_LAUNCH(debug, st, "render_bwd_kernel");
   return GSB_OK;
 }

@@ -2,40 +2,47 @@
 // external operator ("Forward blend").
 //
 // One CTA per 16x16 tile, 8 warps; warp w owns an 8x4 pixel block so that a small splat
-// overlaps few warps.  Instances are gathered (point_list -> 48 B Geom record, L2-resident)
-// straight into shared memory with cp.async, double-buffered in batches of 256 so the gather
-// of batch b+1 overlaps the blend of batch b.  Each warp first votes which of the 256 staged
-// instances can reach any of ITS 32 pixels (conservative extent test, see preprocess.cu) and
-// only evaluates those, in list order, so results are identical to evaluating all of them.
-// A warp stops when all of its pixels are saturated; the CTA stops when all warps have.
+// overlaps few warps.  The warps of a CTA are fully INDEPENDENT (no __syncthreads): each walks
+// the tile's sorted instance list in chunks of 32, gathering point_list -> 48 B Geom record
+// (L2-resident) into its own shared-memory ring with cp.async, STAGES chunks ahead of the
+// blend.  Lane l first tests whether instance l of the chunk can reach any of the warp's 32
+// pixels (conservative extent test, see preprocess.cu); the ballot gives the hit list and only
+// hits are evaluated, in list order, so results are identical to evaluating everything.  A
+// warp stops as soon as all of its pixels are saturated.  (r1a profile of the block-synchronous
+// version: 44 % of issue stalls were CTA barriers — warps waiting for the busiest sibling.)
 #include "gsb_common.cuh"
 
 namespace gsb {
 
 namespace {
 
-constexpr int BATCH = 256;
+constexpr int WARPS = 8;
+constexpr int HB = 4;          // hits evaluated together (ILP)
+#ifndef GSB_FWD_STAGES
+#define GSB_FWD_STAGES 4
+#endif
+constexpr int STAGES = GSB_FWD_STAGES;   // chunks in flight per warp (power of two)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(WARPS * 32)
 render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
-                  const uint2* __restrict__ ranges, float* __restrict__ out_color,
+                  const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                  float* __restrict__ out_color,
                   float* __restrict__ out_depth, float* __restrict__ out_alpha,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
-  __shared__ float4 s_a[2][BATCH];  // x, y, conA, conB
-  __shared__ float4 s_b[2][BATCH];  // conC, opacity, depth, r
-  __shared__ float4 s_c[2][BATCH];  // g, b, extx, exty
+  extern __shared__ float4 smem_dyn[];             // 12 KB per stage per CTA
+  float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
 
-  const int tile = blockIdx.x;
+  const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
   const int pix_x = tx * TILE_X + wx + (lane & 7);
   const int pix_y = ty * TILE_Y + wy + (lane >> 3);
@@ -45,85 +52,90 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 
   const uint2 range = ranges[tile];
   const int n = (int)(range.y - range.x);
-  const int rounds = (n + BATCH - 1) / BATCH;
+  const int chunks = (n + 31) >> 5;
+  const uint32_t* pl = point_list + range.x;
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f, A = 0.f;
   uint32_t last = 0;
   bool done = !inside;
-  bool warp_done = __all_sync(0xffffffffu, done);
 
-  auto issue = [&](int b, uint32_t gid) {
-    const int e = b * BATCH + tid;
-    if (e < n) {
-      const float4* src = reinterpret_cast<const float4*>(geom + gid);
-      const int buf = b & 1;
-      cp_async16(&s_a[buf][tid], src);
-      cp_async16(&s_b[buf][tid], src + 1);
-      cp_async16(&s_c[buf][tid], src + 2);
-    }
-    cp_async_commit();
-  };
-  auto fetch_gid = [&](int b) -> uint32_t {
-    const int e = b * BATCH + tid;
-    return (b < rounds && e < n) ? point_list[range.x + e] : 0u;
-  };
-
-  if (rounds > 0) {
-    issue(0, fetch_gid(0));
-    uint32_t gid_next = fetch_gid(1);
-    for (int b = 0; b < rounds; ++b) {
-      if (b + 1 < rounds) {
-        issue(b + 1, gid_next);
-        gid_next = fetch_gid(b + 2);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      const int buf = b & 1;
-      const int cnt = min(BATCH, n - b * BATCH);
-      if (!warp_done) {
-        for (int j = 0; j < BATCH / 32; ++j) {
-          if (j * 32 >= cnt) break;
-          const int e = j * 32 + lane;
-          bool hit = false;
-          if (e < cnt) {
-            const float4 a = s_a[buf][e];
-            const float4 c = s_c[buf][e];
-            hit = (fabsf(a.x - cxw) <= c.z + 3.5f) && (fabsf(a.y - cyw) <= c.w + 1.5f);
-          }
-          uint32_t mask = __ballot_sync(0xffffffffu, hit);
-          while (mask) {
-            const int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int e2 = j * 32 + k;
-            const float4 a = s_a[buf][e2];
-            const float4 q = s_b[buf][e2];
-            const float4 c = s_c[buf][e2];
-            if (!done) {
-              const float dx = a.x - pxf, dy = a.y - pyf;
-              const float power = -0.5f * (a.z * dx * dx + q.x * dy * dy) - a.w * dx * dy;
-              if (power <= 0.0f) {
-                const float alpha = fminf(ALPHA_CAP, q.y * __expf(power));
-                if (alpha >= ALPHA_MIN) {
-                  const float test_T = T * (1.0f - alpha);
-                  if (test_T < T_MIN) {
-                    done = true;
-                  } else {
-                    const float w = alpha * T;
-                    C0 += q.w * w; C1 += c.x * w; C2 += c.y * w;
-                    Dz += q.z * w; A += w;
-                    T = test_T;
-                    last = (uint32_t)(b * BATCH + e2 + 1);
-                  }
-                }
-              }
-            }
-          }
-          if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+  if (chunks > 0 && !__all_sync(0xffffffffu, done)) {
+    float4 (*ring)[3][32] = s_rec[warp];
+    auto issue = [&](int c, uint32_t gid) {      // stage chunk c (lane's instance) into the ring
+      if (c < chunks) {
+        if (c * 32 + lane < n) {
+          const float4* src = reinterpret_cast<const float4*>(geom + gid);
+          float4 (*st)[32] = ring[c & (STAGES - 1)];
+          cp_async16(&st[0][lane], src);
+          cp_async16(&st[1][lane], src + 1);
+          cp_async16(&st[2][lane], src + 2);
         }
       }
-      if (__syncthreads_and(warp_done)) break;
+      cp_async_commit();                         // always commit: keeps the group count uniform
+    };
+    auto fetch_gid = [&](int c) -> uint32_t {
+      const int e = c * 32 + lane;
+      return (c < chunks && e < n) ? pl[e] : 0u;
+    };
+    // prologue: STAGES-1 chunks in flight, ids of the next one in a register
+#pragma unroll
+    for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_gid(c));
+    uint32_t gid_next = fetch_gid(STAGES - 1);
+
+    for (int c = 0; c < chunks; ++c) {
+      issue(c + STAGES - 1, gid_next);
+      gid_next = fetch_gid(c + STAGES);
+      cp_async_wait<STAGES - 1>();               // chunk c has landed (for this lane)
+      __syncwarp();                              // ... and for every lane of the warp
+      float4 (*st)[32] = ring[c & (STAGES - 1)];
+      const int e = c * 32 + lane;
+      bool hit = false;
+      if (e < n) {
+        const float4 a = st[0][lane];
+        hit = (fabsf(a.x - cxw) <= a.z + 3.5f) && (fabsf(a.y - cyw) <= a.w + 1.5f);
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      // Hits are taken four at a time: the four alphas (LDS, conic, ex2) are independent and
+      // overlap; only the short transmittance chain is applied in order.
+      while (mask) {
+        int k[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          k[i] = mask ? __ffs(mask) - 1 : -1;
+          mask &= mask - 1;
+        }
+        float al[HB];
+        float4 ff[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          al[i] = 0.0f;
+          if (k[i] >= 0) {
+            const float4 a = st[0][k[i]];     // x, y, -, -
+            const float4 q = st[1][k[i]];     // conA, conB, conC, opacity
+            ff[i] = st[2][k[i]];              // depth, r, g, b
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
+            al[i] = power <= 0.0f ? fminf(ALPHA_CAP, q.w * __expf(power)) : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          if (k[i] >= 0 && !done && al[i] >= ALPHA_MIN) {
+            const float test_T = T * (1.0f - al[i]);
+            if (test_T < T_MIN) {
+              done = true;
+            } else {
+              const float w = al[i] * T;
+              C0 += ff[i].y * w; C1 += ff[i].z * w; C2 += ff[i].w * w;
+              Dz += ff[i].x * w; A += w;
+              T = test_T;
+              last = (uint32_t)(c * 32 + k[i] + 1);
+            }
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+      __syncwarp();                              // ring slot c is free before it is refilled
     }
     cp_async_wait<0>();
   }
@@ -144,11 +156,20 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 }  // namespace
 
 int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
-                      const uint2* ranges, float* color, float* depth, float* alpha,
+                      const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
                       uint32_t* n_contrib, float* final_T, bool debug, cudaStream_t st) {
   const int T = v.gx * v.gy;
   if (T == 0) return GSB_OK;
-  render_fwd_kernel<<<T, 256, 0, st>>>(v, geom, point_list, ranges, color, depth, alpha, n_contrib, final_T);
+  constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4);
+  static bool configured[64] = {};   // the attribute is per device
+  int dev = 0;
+  GSB_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev & 63] = true;
+  }
+  render_fwd_kernel<<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth, alpha,
+                                              n_contrib, final_T);
   GSB_POST_LAUNCH(debug, st, "render_fwd_kernel");
   return GSB_OK;
 }

@@ -125,7 +125,7 @@ def make_cloud(num_points: int, sh_degree: int = 0, seed: int = 0) -> Cloud:
     K = (sh_degree + 1) ** 2
     f_dc = (rng.uniform(0, 1, size=(num_points, 1, 3)) - 0.5) / SH_C0
     f_rest = rng.normal(0, 0.05, size=(num_points, K - 1, 3))
-    t = lambda a: torch.tensor(a, dtype=torch.float32)
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32).contiguous()
     return Cloud(t(pts), t(f_dc), t(f_rest), t(scaling), t(rotation), t(opacity), sh_degree)
 
 

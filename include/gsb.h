@@ -55,13 +55,14 @@ typedef struct GsbSettings {
  * `scratch` is transient within one call and may be shared by all calls on one stream. */
 typedef struct GsbLayout {
   size_t saved_bytes;
-  size_t off_geom;        /* P x 48 B  GsbGeom record {x,y,conA,conB | conC,opacity,depth,r | g,b,extx,exty} */
+  size_t off_geom;        /* P x 48 B  GsbGeom record {x,y,extx,exty | conA,conB,conC,opacity | depth,r,g,b} */
   size_t off_clamped;     /* P x u8    SH clamp mask (bit c: channel c clamped at 0) */
   size_t off_counts;      /* 8 x u32   [0]=D (num_rendered) [1]=overflow flag [2]=#visible [3]=max tiles per Gaussian */
   size_t off_point_list;  /* D_cap x u32  Gaussian index per sorted instance */
   size_t off_ranges;      /* T x {u32 start,u32 end} */
   size_t off_n_contrib;   /* H*W x u32 */
   size_t off_final_T;     /* H*W x f32 */
+  size_t off_tile_order;  /* T x u32  tile ids, heaviest first (CTA scheduling order of the blend kernels) */
   size_t scratch_bytes;
   size_t off_rect;        /* P x {u16 minx,miny,maxx,maxy} */
   size_t off_tiles;       /* P x u32  tiles_touched */

@@ -67,9 +67,9 @@ def test_forward_exact_and_tolerance(cuda_device, name, mode):
     geom = sv.geom().cpu()
     vis = g.visible
     assert torch.equal(geom[vis][:, 0:2], g.xy[vis]), "pixel centres differ"
-    assert torch.equal(geom[vis][:, 6], g.depth[vis]), "depths differ"
-    torch.testing.assert_close(geom[vis][:, [2, 3, 4]], g.conic[vis], rtol=1e-6, atol=0)
-    torch.testing.assert_close(geom[vis][:, [7, 8, 9]], g.rgb[vis], rtol=1e-5, atol=1e-6)
+    assert torch.equal(geom[vis][:, 8], g.depth[vis]), "depths differ"
+    torch.testing.assert_close(geom[vis][:, [4, 5, 6]], g.conic[vis], rtol=1e-6, atol=0)
+    torch.testing.assert_close(geom[vis][:, [9, 10, 11]], g.rgb[vis], rtol=1e-5, atol=1e-6)
     # images
     assert (color.cpu() - ref["color"]).abs().max().item() <= FWD_ATOL
     assert (depth.cpu() - ref["depth"]).abs().max().item() <= FWD_ATOL
