@@ -1,0 +1,133 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gsb.h declares; host-side
+logic that needs no device (layout arithmetic, argument errors, view sharding)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from gaussianip_b200 import _lib, build
+    build.build()                      # nvcc cross-compiles sm_100a without a GPU
+    return _lib.load()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gsb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libgsb.so does not export {n}"
+    from gaussianip_b200 import _lib
+    assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
+
+
+def test_abi_version_and_strerror(lib):
+    assert lib.gsb_abi_version() == 1
+    assert lib.gsb_strerror(0) == b"ok"
+    assert b"invalid" in lib.gsb_strerror(-1)
+
+
+def test_layout_is_consistent(lib):
+    from gaussianip_b200 import _lib
+    L = _lib.layout(1000, 100, 150, 5000)
+    offs = [(n, getattr(L, n)) for n in _lib._LAYOUT_FIELDS if n.startswith("off_")]
+    for n, o in offs:
+        assert o % 256 == 0, n
+    saved = [o for n, o in offs if n in ("off_geom", "off_clamped", "off_counts", "off_point_list", "off_ranges",
+                                         "off_n_contrib", "off_final_T", "off_tile_order")]
+    assert saved == sorted(saved) and max(saved) < L.saved_bytes
+    assert L.off_clamped - L.off_geom >= 1000 * 48
+    assert L.off_ranges - L.off_point_list >= 5000 * 4
+    T = ((150 + 15) // 16) * ((100 + 15) // 16)
+    assert L.off_n_contrib - L.off_ranges >= T * 8
+    assert L.scratch_bytes > L.off_ggrad + 1000 * 48 - 1
+    # growth is monotone in every argument
+    assert _lib.layout(2000, 100, 150, 5000).saved_bytes > L.saved_bytes
+    assert _lib.layout(1000, 100, 150, 9000).scratch_bytes > L.scratch_bytes
+
+
+def test_invalid_arguments_return_codes(lib):
+    from gaussianip_b200 import _lib
+    L = _lib.GsbLayout()
+    assert lib.gsb_layout(-1, 10, 10, 10, C.byref(L)) == _lib.GSB_E_INVALID
+    assert lib.gsb_layout(10, 0, 10, 10, C.byref(L)) == _lib.GSB_E_INVALID
+    assert lib.gsb_layout(10, 10, 10, 1 << 40, C.byref(L)) == _lib.GSB_E_UNSUPPORTED
+    s = _lib.GsbSettings()            # all-null settings
+    assert lib.gsb_render_fwd(C.byref(s), 1, None, 0, None, None, None, None) == _lib.GSB_E_INVALID
+    assert lib.gsb_radix_sort_pairs_u32(-5, None, None, None, None, 32, None, None) == _lib.GSB_E_INVALID
+    with pytest.raises(_lib.GsbError):
+        _lib.check(-1, "unit test")
+
+
+def test_rasterizer_argument_errors_without_gpu():
+    from gaussianip_b200 import rasterizer as R
+    rs = R.GaussianRasterizationSettings(32, 32, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                         torch.zeros(3), False, False)
+    r = R.GaussianRasterizer(rs)
+    z = lambda *s: torch.zeros(*s)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=z(4, 3), means2D=z(4, 3), opacities=z(4, 1), scales=z(4, 3), rotations=z(4, 4))
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=z(4, 3), means2D=z(4, 3), opacities=z(4, 1), shs=z(4, 1, 3), colors_precomp=z(4, 3),
+          scales=z(4, 3), rotations=z(4, 4))
+    with pytest.raises(Exception, match="scale/rotation pair"):
+        r(means3D=z(4, 3), means2D=z(4, 3), opacities=z(4, 1), colors_precomp=z(4, 3), scales=z(4, 3),
+          rotations=z(4, 4), cov3D_precomp=z(4, 6))
+    # CPU tensors are refused loudly: there is no CPU fallback
+    with pytest.raises(ValueError, match="CUDA"):
+        r(means3D=z(4, 3), means2D=z(4, 3), opacities=z(4, 1), colors_precomp=z(4, 3), scales=z(4, 3),
+          rotations=z(4, 4))
+    assert R.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_import_shim_resolves_reference_import():
+    import diff_gaussian_rasterization as d
+    from gaussianip_b200 import rasterizer as R
+    assert d.GaussianRasterizer is R.GaussianRasterizer
+    assert d.GaussianRasterizationSettings is R.GaussianRasterizationSettings
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gaussianip_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("CPU oracle", "").replace("the oracle", ""), fn
+
+
+def test_shard_views():
+    from gaussianip_b200.multiview import shard_views
+    for world in (1, 2, 4, 8):
+        got = sorted(v for r in range(world) for v in shard_views(64, r, world))
+        assert got == list(range(64))
+        sizes = {len(shard_views(64, r, world)) for r in range(world)}
+        assert sizes == {64 // world}
+    assert shard_views(4, 5, 8) == []
+    with pytest.raises(ValueError):
+        shard_views(4, 2, 2)
+
+
+def test_synthetic_workload_shapes():
+    from gaussianip_b200 import synthetic
+    cl = synthetic.make_cloud(5000, 3, 0)
+    assert cl.xyz.shape == (5000, 3) and cl.features_rest.shape == (5000, 15, 3) and cl.xyz.is_contiguous()
+    ext = (cl.xyz.max(0).values - cl.xyz.min(0).values)
+    assert abs(float(ext.max()) - synthetic.BODY_EXTENT) < 0.05       # poser.py:808-821 normalisation
+    assert int(ext.argmax()) == 2                                     # z-up
+    cams = synthetic.ahds_cameras(4, 64, 64)
+    assert len(cams) == 4 and cams[0].world_view_transform.shape == (4, 4)
+    assert len(synthetic.vcr_cameras(64, 32, 32)) == 64
+    assert len(synthetic.playback_cameras(136, 32, 32)) == 136

@@ -1,0 +1,113 @@
+"""CPU, world_size 2, gloo: the view-sharded step (flat gradient bucket all-reduce + radii max +
+densification statistics) equals the single-process loop over all views."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gaussianip_b200 import multiview
+
+P, V = 257, 6
+
+
+def _make_params():
+    g = torch.Generator().manual_seed(0)
+    return {"xyz": torch.randn(P, 3, generator=g), "features_dc": torch.randn(P, 1, 3, generator=g),
+            "opacity": torch.randn(P, 1, generator=g), "scaling": torch.randn(P, 3, generator=g),
+            "rotation": torch.randn(P, 4, generator=g)}
+
+
+def _render(params, v, vsp):
+    """Stand-in for the CUDA op with the same autograd structure: depends on every parameter and
+    on the zero-valued screen-space carrier; per-view radii."""
+    g = torch.Generator().manual_seed(100 + v)
+    w = torch.randn(P, 3, generator=g)
+    img = (params["xyz"] * w).sum(1) * torch.sigmoid(params["opacity"][:, 0]) \
+        + (torch.exp(params["scaling"]) * w).sum(1) + params["features_dc"][:, 0, :].sum(1) * (v + 1) \
+        + torch.nn.functional.normalize(params["rotation"])[:, 0] + (vsp * w * (v + 2)).sum(1)
+    radii = (torch.rand(P, generator=g) * 30).to(torch.int32) * (torch.rand(P, generator=g) > 0.3)
+    return {"render": img, "radii": radii.to(torch.int32)}
+
+
+def _loss(v, out):
+    return (out["render"] ** 2).sum() * (0.5 + v)
+
+
+def _run_step(group=None):
+    params = {k: t.clone().requires_grad_(True) for k, t in _make_params().items()}
+    vp = multiview.ViewParallel(params, P, group)
+    res = vp.step(V, lambda v, vsp: _render(params, v, vsp), _loss)
+    acc, den, mr = torch.zeros(P, 1), torch.zeros(P, 1), torch.zeros(P)
+    vis = multiview.add_densification_stats(acc, den, mr, res["viewspace_grad"], res["radii"])
+    return vp, res, acc, den, mr, vis
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vp, res, acc, den, mr, vis = _run_step()
+        assert res["local_views"] == list(range(rank, V, world))
+        ret[rank] = {"flat": vp.bucket.flat.clone(), "radii": res["radii"].clone(), "loss": res["loss"].clone(),
+                     "acc": acc, "den": den, "mr": mr, "vis": vis}
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_step_equals_single_process():
+    vp1, res1, acc1, den1, mr1, vis1 = _run_step()           # world = 1: all views locally
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in (0, 1):
+        got = ret[r]
+        torch.testing.assert_close(got["flat"], vp1.bucket.flat, rtol=1e-4, atol=1e-4)
+        assert torch.equal(got["radii"], res1["radii"])
+        torch.testing.assert_close(got["loss"], res1["loss"], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(got["acc"], acc1, rtol=1e-5, atol=1e-5)
+        assert torch.equal(got["den"], den1) and torch.equal(got["mr"], mr1) and torch.equal(got["vis"], vis1)
+    assert torch.equal(ret[0]["flat"], ret[1]["flat"])       # replicas stay bit-identical
+
+
+def test_bucket_views_alias_leaf_grads():
+    params = {k: t.clone().requires_grad_(True) for k, t in _make_params().items()}
+    b = multiview.GradBucket(params, P)
+    b.attach()
+    assert b.nbytes() == 4 * (P * (3 + 3 + 1 + 3 + 4) + P * 3)
+    (params["xyz"].sum() * 2 + (b.viewspace_points * 3).sum()).backward()
+    (params["xyz"].sum() * 5).backward()                      # accumulates in place into the bucket
+    assert params["xyz"].grad.data_ptr() == b.views["xyz"].data_ptr()
+    assert float(b.views["xyz"].min()) == 7.0 and float(b.viewspace_grad().max()) == 3.0
+    b.zero_()
+    assert float(params["xyz"].grad.abs().max()) == 0.0
+
+
+def test_densification_stats_match_reference_formulas():
+    """gaussian_model.py:420-422 and GaussianIP.py:456 on explicit tensors."""
+    g = torch.Generator().manual_seed(3)
+    grad = torch.randn(P, 3, generator=g)
+    radii = ((torch.rand(P, generator=g) * 40).to(torch.int32)) * (torch.rand(P, generator=g) > 0.5)
+    acc, den, mr = torch.rand(P, 1, generator=g), torch.ones(P, 1), torch.rand(P, generator=g) * 20
+    acc0, den0, mr0 = acc.clone(), den.clone(), mr.clone()
+    vis = multiview.add_densification_stats(acc, den, mr, grad, radii.to(torch.int32))
+    f = radii > 0
+    exp_acc, exp_den, exp_mr = acc0.clone(), den0.clone(), mr0.clone()
+    exp_acc[f] += torch.norm(grad[f, :2], dim=-1, keepdim=True)
+    exp_den[f] += 1
+    exp_mr[f] = torch.max(mr0[f], radii[f].float())
+    assert torch.equal(vis, f)
+    torch.testing.assert_close(acc, exp_acc)
+    assert torch.equal(den, exp_den) and torch.equal(mr, exp_mr)
