@@ -241,14 +241,20 @@ def main():
     vp = multiview.ViewParallel(params, a.points)
     model = Model(params)
 
-    def loss_of(v, out):
-        w = weights[v]
-        return (out["render"] * w[0]).sum() + (out["depth_3dgs"] * w[1]).sum() + (out["alpha_3dgs"] * w[2]).sum()
+    w_color = torch.stack([w[0] for w in weights])
+    w_depth = torch.stack([w[1] for w in weights])
+    w_alpha = torch.stack([w[2] for w in weights])
+
+    def loss_of(views, out):
+        return (out["render"] * w_color).sum() + (out["depth_3dgs"] * w_depth).sum() + \
+            (out["alpha_3dgs"] * w_alpha).sum()
 
     def run_step(step_idx, cams):
-        def render_fn(v, vsp):
-            return renderer.render(cams[v], model, None, bg, screenspace_points=vsp)
-        return vp.step(a.views, render_fn, loss_of, views=range(a.views))
+        # public API: all views of the step in one batched render call (same kernels per view as
+        # the single-view operator; activations evaluated once per step, one autograd node)
+        def render_views_fn(views, vsp):
+            return renderer.render_views([cams[v] for v in views], model, None, bg, screenspace_points=vsp)
+        return vp.step_batched(a.views, render_views_fn, loss_of, views=range(a.views))
 
     def device_cams(step_idx):
         return [Camera(c2w, fovy, a.res, a.res, data_device=dev) for c2w, fovy in cam_specs[step_idx]]

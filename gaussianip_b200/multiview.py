@@ -65,7 +65,7 @@ class GradBucket:
         for k, p in self.params.items():
             if p.dtype != torch.float32:
                 raise ValueError(f"{k}: bucket holds fp32 gradients only")
-            p.grad = self.views[k]
+            p.grad = self.views[k] if p.numel() else torch.zeros_like(p)
         self.viewspace_points.grad = self.views[self.VIEWSPACE]
 
     def zero_(self) -> None:
@@ -129,6 +129,30 @@ class ViewParallel:
             loss = loss_fn(v, out)
             loss.backward()            # accumulates into the bucket views, view after view
             total = total + loss.detach()
+        b.all_reduce(self.group)
+        all_reduce_radii_max(radii, self.group)
+        if self.world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return {"loss": total, "radii": radii, "viewspace_grad": b.viewspace_grad(), "local_views": local}
+
+    def step_batched(self, n_views: int, render_views_fn: Callable, loss_fn: Callable,
+                     views: Optional[Sequence[int]] = None):
+        """Same exchange, but the local views go through ONE batched render call:
+        render_views_fn(local_view_indices, viewspace_points) -> dict with 'radii' (max over the
+        local views) and stacked outputs; loss_fn(local_view_indices, dict) -> scalar."""
+        b = self.bucket
+        b.zero_()
+        b.attach()
+        local = shard_views(n_views, self.rank, self.world) if views is None else list(views)
+        if local:
+            out = render_views_fn(local, b.viewspace_points)
+            radii = out["radii"]
+            loss = loss_fn(local, out)
+            loss.backward()
+            total = loss.detach().to(torch.float32)
+        else:
+            radii = torch.zeros(self.n_points, dtype=torch.int32, device=b.device)
+            total = torch.zeros((), dtype=torch.float32, device=b.device)
         b.all_reduce(self.group)
         all_reduce_radii_max(radii, self.group)
         if self.world > 1:

@@ -167,7 +167,7 @@ class _Saved:
         return out[:self.num_rendered]
 
 
-def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D):
+def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):
     lib = _lib.load()
     device = means3D.device
     if device.type != "cuda":
@@ -179,10 +179,13 @@ def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D)
         ws = _workspace(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         s, keep = _make_settings(rs, device)
-        color = torch.empty(3, H, W, dtype=torch.float32, device=device)
-        depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
-        alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
-        radii = torch.empty(P, dtype=torch.int32, device=device)
+        if out is not None:
+            color, radii, depth, alpha = out           # caller-owned contiguous slices
+        else:
+            color = torch.empty(3, H, W, dtype=torch.float32, device=device)
+            depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
+            alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
+            radii = torch.empty(P, dtype=torch.int32, device=device)
         while True:
             d_cap = ws.capacity_for(P)
             L = _lib.layout(P, H, W, d_cap)
@@ -306,6 +309,79 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.sv = None
         return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
                 out["rotations"], out["cov3D"], None)
+
+
+class _RasterizeViews(torch.autograd.Function):
+    """V views of the same Gaussians in one autograd node (additive API).
+
+    Every view runs exactly the kernels of the single-view operator; what changes is the host
+    side: one node instead of V, outputs written into slices of stacked tensors, and the
+    backward of view v > 0 ACCUMULATES (beta = 1) into the gradients view 0 wrote, so the sum
+    over views — which is what the optimiser and the densification statistics consume
+    (threestudio/systems/GaussianIP.py:450-457) — is formed inside preprocess_bwd instead of by
+    V autograd AccumulateGrad passes per tensor."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                settings_list):
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = _prepare_inputs(
+            means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        V = len(settings_list)
+        if V == 0:
+            raise ValueError("no views")
+        H, W = int(settings_list[0].image_height), int(settings_list[0].image_width)
+        for rs in settings_list:
+            if (int(rs.image_height), int(rs.image_width)) != (H, W):
+                raise ValueError("all views of one call must have the same resolution")
+        dev, P = means3D.device, means3D.shape[0]
+        color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
+        depth = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
+        alpha = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(V, P, dtype=torch.int32, device=dev)
+        svs = []
+        for v, rs in enumerate(settings_list):
+            _, _, _, _, sv = _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
+                                           cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]))
+            svs.append(sv)
+        ctx.settings_list, ctx.svs = list(settings_list), svs
+        ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,
+                       cov3Ds_precomp is not None)
+        e = means3D.new_empty(0)
+        ctx.save_for_backward(means3D, sh if sh is not None else e,
+                              colors_precomp if colors_precomp is not None else e, opacities,
+                              scales if scales is not None else e, rotations if rotations is not None else e,
+                              cov3Ds_precomp if cov3Ds_precomp is not None else e, radii)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        means3D, sh, colors, opacities, scales, rotations, cov3D, radii = ctx.saved_tensors
+        has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
+        out = None
+        for v, (rs, sv) in enumerate(zip(ctx.settings_list, ctx.svs)):
+            out = _backward_impl(rs, sv, means3D, sh if has_sh else None, colors if has_col else None, opacities,
+                                 scales if has_sc else None, rotations if has_rot else None,
+                                 cov3D if has_cov else None, radii[v],
+                                 None if grad_color is None else grad_color[v],
+                                 None if grad_depth is None else grad_depth[v],
+                                 None if grad_alpha is None else grad_alpha[v], out=out, accumulate=v > 0)
+        ctx.svs = None
+        return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
+                out["rotations"], out["cov3D"], None)
+
+
+def rasterize_views(settings_list, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                    rotations=None, cov3D_precomp=None):
+    """Batched form of GaussianRasterizer(...)(...): returns stacked (color [V,3,H,W], radii [V,P],
+    depth [V,1,H,W], alpha [V,1,H,W]); means2D.grad receives the SUM over views."""
+    if (shs is None) == (colors_precomp is None):
+        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+    if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+            ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+        raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+    return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                 cov3D_precomp, tuple(settings_list))
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

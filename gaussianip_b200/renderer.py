@@ -19,7 +19,7 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
 
 SH_C0 = 0.28209479177387814
 
@@ -88,6 +88,48 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
 
 render_with_smaller_scale = render
+
+
+def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+                 screenspace_points=None):
+    """All views of one optimisation step in ONE call (additive API; the reference loops
+    ``render`` over the views in Python, threestudio/systems/GaussianIP.py:154-159, 305-307).
+
+    Same per-view semantics as ``render``; the differences are host-side only: the activation
+    getters (exp / sigmoid / normalize / cat, gaussian_model.py:84-107) run once per step instead
+    of once per view, there is one autograd node, and ``viewspace_points.grad`` receives the sum
+    over views directly.  Returns the ``render`` dictionary with a leading view axis:
+    render [V,3,H,W], depth_3dgs / alpha_3dgs [V,1,H,W], radii_per_view [V,P], radii = max over
+    views [P], visibility_filter = radii > 0."""
+    xyz = _get(pc, "get_xyz")
+    if screenspace_points is None:
+        screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
+    sh_degree = getattr(pc, "active_sh_degree", getattr(pc, "sh_degree", 0))
+    settings = [_settings(cam, bg_color, scaling_modifier, sh_degree) for cam in cameras]
+    scales = rotations = cov3D_precomp = None
+    if pipe is not None and getattr(pipe, "compute_cov3D_python", False):
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales, rotations = _get(pc, "get_scaling"), _get(pc, "get_rotation")
+    shs = colors_precomp = None
+    if override_color is not None:
+        colors_precomp = override_color
+    elif pipe is not None and getattr(pipe, "convert_SHs_python", False):
+        raise ValueError("convert_SHs_python is per view (colours depend on the camera); use render()")
+    else:
+        shs = _get(pc, "get_features")
+    f = lambda t: None if t is None else t.float()
+    image, radii_v, depth, alpha = rasterize_views(
+        settings, means3D=xyz.float(), means2D=screenspace_points.float(), shs=f(shs),
+        colors_precomp=colors_precomp, opacities=_get(pc, "get_opacity").float(), scales=f(scales),
+        rotations=f(rotations), cov3D_precomp=cov3D_precomp)
+    radii = radii_v.max(dim=0).values
+    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+            "radii": radii, "radii_per_view": radii_v, "depth_3dgs": depth, "alpha_3dgs": alpha}
 
 
 def render_deformed(viewpoint_camera, means3D, feats, opacity, scales, rotations, active_sh_degree, pipe,

@@ -235,3 +235,45 @@ def test_capacity_growth_retry(cuda_device):
     assert len(ref["binning"].keys) > (1 << 16)
     assert ws.retries == before + 1
     assert (got["color"].cpu() - ref["color"]).abs().max().item() <= FWD_ATOL
+
+
+def test_batched_views_equal_per_view_calls(cuda_device):
+    """rasterize_views (one autograd node, beta=1 gradient accumulation) == looping the
+    single-view operator: forward bit-identical, gradients = sum over views."""
+    from gaussianip_b200 import rasterizer as R, synthetic
+    dev = cuda_device
+    H = W = 96
+    scene = util.humanoid_scene(P=3000, H=H, W=W, sh_degree=1)
+    cams = synthetic.ahds_cameras(3, H, W, seed=5, device=dev)
+    settings = [R.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, scene.bg.to(dev), 1.0,
+                                                c.world_view_transform, c.full_proj_transform, 1,
+                                                c.camera_center, False, False) for c in cams]
+    ws = [util.loss_weights(H, W, seed=10 + i) for i in range(3)]
+
+    def leaves():
+        d = scene.inputs(dev, requires_grad=True)
+        d["means2D"].retain_grad()
+        return d
+
+    a = leaves()
+    outs = []
+    loss = 0
+    for rs, w in zip(settings, ws):
+        o = R.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=a["means2D"], shs=a["shs"], opacities=a["opacities"],
+                                     scales=a["scales"], rotations=a["rotations"])
+        outs.append(o)
+        loss = loss + (o[0] * w[0].to(dev)).sum() + (o[2] * w[1].to(dev)).sum() + (o[3] * w[2].to(dev)).sum()
+    loss.backward()
+    b = leaves()
+    color, radii, depth, alpha = R.rasterize_views(settings, means3D=b["means3D"], means2D=b["means2D"],
+                                                   shs=b["shs"], opacities=b["opacities"], scales=b["scales"],
+                                                   rotations=b["rotations"])
+    for v in range(3):
+        assert torch.equal(color[v], outs[v][0]) and torch.equal(radii[v], outs[v][1])
+        assert torch.equal(depth[v], outs[v][2]) and torch.equal(alpha[v], outs[v][3])
+    wc = torch.stack([w[0] for w in ws]).to(dev)
+    wd = torch.stack([w[1] for w in ws]).to(dev)
+    wa = torch.stack([w[2] for w in ws]).to(dev)
+    ((color * wc).sum() + (depth * wd).sum() + (alpha * wa).sum()).backward()
+    for k in ("means3D", "means2D", "shs", "opacities", "scales", "rotations"):
+        _grad_close(k, b[k].grad, a[k].grad, rtol=2e-5)
