@@ -1,8 +1,8 @@
 // Stage 2: binning.  Replaces InclusiveSum + duplicateWithKeys + cub::DeviceRadixSort +
 // identifyTileRanges of the external operator ("Binning") with
-// hand-written kernels: a stable LSD radix sort (8-bit digits; per-block histograms,
-// row scan, match-based stable in-block ranking), a gathered scan + instance emission, and a
-// tile-boundary pass.
+// hand-written kernels: a stable onesweep LSD radix sort (8-bit digits; global histograms
+// once, one kernel per pass with decoupled look-back, match-based stable in-block ranking), a
+// gathered scan + instance emission, and a tile-boundary pass.
 //
 // Two modes produce the IDENTICAL instance order (tile, then depth bits, then Gaussian id):
 //   GSB_BIN_TWO_LEVEL  sort the P Gaussians once by 32-bit depth key (4 passes over P), emit
@@ -20,8 +20,8 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 16;
-constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per block
+constexpr int RS_IPT = 8;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 2048 keys per block
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
@@ -38,6 +38,20 @@ __device__ __forceinline__ long long load_n(const uint32_t* d_n, long long n_cap
 template <typename KeyT>
 __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift) {
   return (uint32_t)(k >> shift) & 0xFFu;
+}
+
+// Lanes of the warp holding the same 8-bit digit (and valid).  Eight ballots, fixed cost:
+// match.any.sync iterates once per DISTINCT value, ~30x slower on random digits (measured r1:
+// 27 us per 1 M-key pass with match.any).
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid) {
+  uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
 }
 
 // exclusive scan of one value per thread over a 256-thread block; returns exclusive prefix,
@@ -65,64 +79,86 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- radix sort -----------------------------------------------------------------------------
+// "Onesweep" organisation: ONE pass over the keys builds the global digit histograms of every
+// pass (they do not depend on the arrangement), then each pass is a single kernel that reads
+// its keys once and writes them once.  A block learns how many keys of each digit precede it
+// from the blocks before it by decoupled look-back over one 32-bit status word per (block,
+// digit): [31:30] = flag (0 not ready, 1 block aggregate, 2 inclusive prefix), [29:0] = count.
+// Block ids are handed out by an atomic counter in arrival order, so a block only ever waits
+// for blocks that are already running.  Stability: the in-block rank follows the original
+// order (warps own consecutive segments, rounds and lanes ascend), blocks are ordered by id.
+
+constexpr uint32_t ST_AGG = 1u << 30, ST_PREFIX = 2u << 30, ST_MASK = (1u << 30) - 1;
+constexpr int MAX_PASSES = 8;
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ d_n, long long n_cap, int shift,
-                  uint32_t* __restrict__ hist, int num_blocks) {
-  __shared__ uint32_t s_h[256];
+radix_global_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ d_n, long long n_cap,
+                         int passes, uint32_t* __restrict__ ghist /*[passes][256]*/) {
+  __shared__ uint32_t s_h[MAX_PASSES][256];
   const long long n = load_n(d_n, n_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  s_h[tid] = 0;
+  const long long block_base = (long long)blockIdx.x * RS_TILE;
+  if (block_base >= n) return;
+  for (int p = 0; p < passes; ++p) s_h[p][tid] = 0;
   __syncthreads();
-  const long long seg = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_IPT * 32);
-  if ((long long)blockIdx.x * RS_TILE < n) {
+  const long long seg = block_base + (long long)warp * (RS_IPT * 32);
+  KeyT kk[RS_IPT];
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {          // all loads in flight before any is consumed
+    const long long idx = seg + r * 32 + lane;
+    kk[r] = idx < n ? keys[idx] : (KeyT)0;
+  }
 #pragma unroll 4
-    for (int r = 0; r < RS_IPT; ++r) {
-      const long long idx = seg + r * 32 + lane;
-      const bool valid = idx < n;
-      const uint32_t d = valid ? digit_of(keys[idx], shift) : 0x100u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_h[d], (uint32_t)__popc(peers));
+  for (int r = 0; r < RS_IPT; ++r) {
+    const long long idx = seg + r * 32 + lane;
+    const bool valid = idx < n;
+    const KeyT k = kk[r];
+    for (int p = 0; p < passes; ++p) {
+      const uint32_t d = digit_of(k, 8 * p);
+      const uint32_t peers = match_digit(d, valid);
+      if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_h[p][d], (uint32_t)__popc(peers));
     }
   }
   __syncthreads();
-  hist[(size_t)tid * num_blocks + blockIdx.x] = s_h[tid];
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t c = s_h[p][tid];
+    if (c) atomicAdd(&ghist[p * 256 + tid], c);
+  }
 }
 
-// one block per digit: in-place exclusive scan of that digit's row of per-block counts
-__global__ void __launch_bounds__(RS_THREADS)
-radix_scan_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ totals, int num_blocks) {
-  __shared__ uint32_t s_warp[RS_WARPS];
-  uint32_t* row = hist + (size_t)blockIdx.x * num_blocks;
-  uint32_t carry = 0;
-  for (int base = 0; base < num_blocks; base += RS_THREADS) {
-    const int i = base + threadIdx.x;
-    const uint32_t v = i < num_blocks ? row[i] : 0;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan_256(v, s_warp, &total);
-    if (i < num_blocks) row[i] = carry + ex;
-    carry += total;
-  }
-  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+template <typename KeyT>
+constexpr size_t onesweep_smem_bytes() {
+  return (size_t)RS_TILE * (sizeof(KeyT) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + RS_WARPS + 4) * sizeof(uint32_t);
 }
 
 template <typename KeyT, bool IOTA>
 __global__ void __launch_bounds__(RS_THREADS)
-radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                     const uint32_t* __restrict__ d_n, long long n_cap, int shift,
-                     const uint32_t* __restrict__ hist, const uint32_t* __restrict__ totals, int num_blocks) {
-  __shared__ uint32_t s_cnt[RS_WARPS][256];
-  __shared__ uint32_t s_warp[RS_WARPS];
+radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                      const uint32_t* __restrict__ d_n, long long n_cap, int shift,
+                      const uint32_t* __restrict__ ghist /*[256] of this pass*/,
+                      volatile uint32_t* __restrict__ status /*[num_blocks][256] of this pass*/,
+                      uint32_t* __restrict__ block_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);                         // block-sorted keys
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + RS_TILE);
+  uint32_t (*s_cnt)[256] = reinterpret_cast<uint32_t (*)[256]>(s_vals + RS_TILE);
+  uint32_t* s_goff = reinterpret_cast<uint32_t*>(s_cnt + RS_WARPS);         // global slot - local slot, per digit
+  uint32_t* s_warp = s_goff + 256;
+  uint32_t* s_bid = s_warp + RS_WARPS;
+
   const long long n = load_n(d_n, n_cap);
-  const long long block_base = (long long)blockIdx.x * RS_TILE;
-  if (block_base >= n) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *s_bid = atomicAdd(block_counter, 1u);
 #pragma unroll
   for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][tid] = 0;
-  const uint32_t dbase = block_exclusive_scan_256(totals[tid], s_warp, nullptr);  // syncs inside
-  const uint32_t gbase = dbase + hist[(size_t)tid * num_blocks + blockIdx.x];
+  // exclusive scan of the global histogram = first output slot of every digit
+  const uint32_t dbase = block_exclusive_scan_256(ghist[tid], s_warp, nullptr);  // syncs inside
+  const uint32_t bid = *s_bid;
+  const long long block_base = (long long)bid * RS_TILE;
+  if (block_base >= n) return;
+  const int count = (int)((n - block_base) < (long long)RS_TILE ? (n - block_base) : (long long)RS_TILE);
 
   KeyT key[RS_IPT];
   uint32_t val[RS_IPT];
@@ -130,14 +166,19 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
   const long long seg = block_base + (long long)warp * (RS_IPT * 32);
   const uint32_t lt = lanemask_lt();
 #pragma unroll
-  for (int r = 0; r < RS_IPT; ++r) {
+  for (int r = 0; r < RS_IPT; ++r) {          // all loads in flight before the ranking rounds
     const long long idx = seg + r * 32 + lane;
     const bool valid = idx < n;
     key[r] = valid ? keys_in[idx] : (KeyT)0;
     val[r] = valid ? (IOTA ? (uint32_t)idx : vals_in[idx]) : 0u;
-    const uint32_t d = valid ? digit_of(key[r], shift) : 0x100u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const long long idx = seg + r * 32 + lane;
+    const bool valid = idx < n;
+    const uint32_t d = digit_of(key[r], shift);
+    const uint32_t peers = match_digit(d, valid);
+    const int leader = valid ? __ffs(peers) - 1 : lane;
     uint32_t old = 0;
     if (valid && lane == leader) {
       old = s_cnt[warp][d];
@@ -149,23 +190,64 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
   }
   __syncthreads();
   {
-    uint32_t run = gbase;
+    // thread tid owns digit tid: exclusive offsets of the warps inside the block, block count
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       const uint32_t c = s_cnt[w][tid];
       s_cnt[w][tid] = run;
       run += c;
     }
+    volatile uint32_t* mine = status + (size_t)bid * 256 + tid;
+    uint32_t excl = 0;
+    if (bid == 0) {
+      *mine = ST_PREFIX | run;
+    } else {
+      *mine = ST_AGG | run;
+      long long j = (long long)bid - 1;
+      bool found = false;
+      while (!found) {                           // four predecessors per round trip
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (j - k >= 0) ? status[(size_t)(j - k) * 256 + tid] : ST_PREFIX;
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (found || used != k) continue;
+          const uint32_t flag = v[k] & ~ST_MASK;
+          if (flag == 0) continue;               // running but not published yet: retry from here
+          excl += v[k] & ST_MASK;
+          used = k + 1;
+          if (flag == ST_PREFIX) found = true;
+        }
+        j -= used;
+      }
+      *mine = ST_PREFIX | (excl + run);
+    }
+    // position of this digit's run inside the block-sorted tile
+    const uint32_t local = block_exclusive_scan_256(run, s_warp, nullptr);   // syncs inside
+    s_goff[tid] = dbase + excl - local;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][tid] += local;
   }
   __syncthreads();
+  // stage the tile in shared memory in sorted order, then write runs of equal digits with
+  // consecutive threads -> consecutive addresses (coalesced instead of one sector per key)
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     const long long idx = seg + r * 32 + lane;
     if (idx < n) {
-      const uint32_t pos = s_cnt[warp][digit_of(key[r], shift)] + rank[r];
-      keys_out[pos] = key[r];
-      vals_out[pos] = val[r];
+      const uint32_t lpos = s_cnt[warp][digit_of(key[r], shift)] + rank[r];
+      s_keys[lpos] = key[r];
+      s_vals[lpos] = val[r];
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < count; i += RS_THREADS) {
+    const KeyT k = s_keys[i];
+    const uint32_t pos = s_goff[digit_of(k, shift)] + (uint32_t)i;
+    keys_out[pos] = k;
+    vals_out[pos] = s_vals[i];
   }
 }
 
@@ -321,9 +403,11 @@ inline int bits_for(unsigned int max_value) {  // bits needed to represent value
 int radix_num_passes(int end_bit) { return (end_bit + 7) / 8; }
 bool radix_result_in_A(int passes) { return (passes & 1) != 0; }
 
+// tmp layout: [MAX_PASSES][256] global histograms | [MAX_PASSES] block counters (padded to 256) |
+//             [MAX_PASSES][num_blocks][256] look-back status words
 size_t radix_tmp_bytes(long long n_cap) {
   const long long nb = (n_cap + RS_TILE - 1) / RS_TILE;
-  return (size_t)(256 * (nb > 0 ? nb : 1) + 256) * sizeof(uint32_t);
+  return (size_t)(MAX_PASSES * 256 + 256 + (size_t)MAX_PASSES * (nb > 0 ? nb : 1) * 256) * sizeof(uint32_t);
 }
 
 // Stable LSD sort on bits [0,end_bit).  Pass 0 reads (src_keys, src_vals); pass p writes
@@ -334,27 +418,43 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
                      KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
                      bool iota_vals, void* tmp, bool debug, cudaStream_t st) {
   if (n_cap <= 0) return GSB_OK;
-  const int nb = (int)((n_cap + RS_TILE - 1) / RS_TILE);
-  uint32_t* hist = static_cast<uint32_t*>(tmp);
-  uint32_t* totals = hist + (size_t)256 * nb;
   const int passes = radix_num_passes(end_bit);
+  if (passes == 0) return GSB_OK;
+  if (passes > MAX_PASSES) return GSB_E_INVALID;
+  const int nb = (int)((n_cap + RS_TILE - 1) / RS_TILE);
+  uint32_t* ghist = static_cast<uint32_t*>(tmp);
+  uint32_t* counters = ghist + MAX_PASSES * 256;
+  uint32_t* status = counters + 256;
+  const size_t used = (size_t)(MAX_PASSES * 256 + 256 + (size_t)passes * nb * 256) * sizeof(uint32_t);
+  GSB_CUDA(cudaMemsetAsync(tmp, 0, used, st));
+  constexpr size_t smem = onesweep_smem_bytes<KeyT>();
+  {
+    static bool configured[64] = {};   // the attribute is per device and per instantiation
+    int dev = 0;
+    GSB_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      configured[dev & 63] = true;
+    }
+  }
+  radix_global_hist_kernel<KeyT><<<nb, RS_THREADS, 0, st>>>(src_keys, d_n, n_cap, passes, ghist);
+  GSB_POST_LAUNCH(debug, st, "radix_global_hist_kernel");
   for (int p = 0; p < passes; ++p) {
     const KeyT* kin = p == 0 ? src_keys : ((p & 1) ? keysA : keysB);
     const uint32_t* vin = p == 0 ? src_vals : ((p & 1) ? valsA : valsB);
     KeyT* kout = (p & 1) ? keysB : keysA;
     uint32_t* vout = (p & 1) ? valsB : valsA;
-    const int shift = 8 * p;
-    radix_hist_kernel<KeyT><<<nb, RS_THREADS, 0, st>>>(kin, d_n, n_cap, shift, hist, nb);
-    GSB_POST_LAUNCH(debug, st, "radix_hist_kernel");
-    radix_scan_kernel<<<256, RS_THREADS, 0, st>>>(hist, totals, nb);
-    GSB_POST_LAUNCH(debug, st, "radix_scan_kernel");
+    uint32_t* stp = status + (size_t)p * nb * 256;
     if (p == 0 && iota_vals)
-      radix_scatter_kernel<KeyT, true><<<nb, RS_THREADS, 0, st>>>(kin, vin, kout, vout, d_n, n_cap, shift,
-                                                                  hist, totals, nb);
+      radix_onesweep_kernel<KeyT, true><<<nb, RS_THREADS, smem, st>>>(kin, vin, kout, vout, d_n, n_cap, 8 * p,
+                                                                      ghist + p * 256, stp, counters + p);
     else
-      radix_scatter_kernel<KeyT, false><<<nb, RS_THREADS, 0, st>>>(kin, vin, kout, vout, d_n, n_cap, shift,
-                                                                   hist, totals, nb);
-    GSB_POST_LAUNCH(debug, st, "radix_scatter_kernel");
+      radix_onesweep_kernel<KeyT, false><<<nb, RS_THREADS, smem, st>>>(kin, vin, kout, vout, d_n, n_cap, 8 * p,
+                                                                       ghist + p * 256, stp, counters + p);
+    GSB_POST_LAUNCH(debug, st, "radix_onesweep_kernel");
   }
   return GSB_OK;
 }
