@@ -85,6 +85,43 @@ class Camera:
         return math.tan(self.FoVy * 0.5)
 
 
+def cameras_from_c2w(c2ws, fovys, height, width, device="cuda"):
+    """Build the Camera objects of one step with ONE pinned staging buffer and ONE asynchronous
+    host->device copy (the reference builds each camera separately with two GPU inversions,
+    threestudio/systems/GaussianIP.py:155; a pageable per-tensor upload would also block the host
+    until the stream drains).  Values are identical to Camera(c2w, fovy, height, width)."""
+    n = len(c2ws)
+    stage = torch.empty(n, 51, dtype=torch.float32)
+    if torch.device(device).type == "cuda":
+        stage = stage.pin_memory()
+    cams = []
+    for i, (c2w, fovy) in enumerate(zip(c2ws, fovys)):
+        cam = Camera.__new__(Camera)
+        fovy = float(fovy)
+        cam.FoVx, cam.FoVy = focal2fov(fov2focal(fovy, height), width), fovy
+        cam.image_height, cam.image_width = int(height), int(width)
+        cam.zfar, cam.znear, cam.trans, cam.scale = 100.0, 0.01, torch.zeros(3), 1.0
+        cam.data_device = torch.device(device)
+        view = _w2c_from_c2w(c2w).T
+        proj = projection_matrix(cam.znear, cam.zfar, cam.FoVx, cam.FoVy).T
+        full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
+        center = np.linalg.inv(view)[3, :3]
+        row = stage[i]
+        row[0:16] = torch.from_numpy(view.reshape(-1).astype(np.float32))
+        row[16:32] = torch.from_numpy(proj.reshape(-1).astype(np.float32))
+        row[32:48] = torch.from_numpy(full.reshape(-1).astype(np.float32))
+        row[48:51] = torch.from_numpy(center.astype(np.float32))
+        cams.append(cam)
+    dev_buf = stage.to(device, non_blocking=True)
+    for i, cam in enumerate(cams):
+        cam.world_view_transform = dev_buf[i, 0:16].view(4, 4)
+        cam.projection_matrix = dev_buf[i, 16:32].view(4, 4)
+        cam.full_proj_transform = dev_buf[i, 32:48].view(4, 4)
+        cam.camera_center = dev_buf[i, 48:51]
+        cam._stage = stage            # keep the pinned buffer alive until the copy has run
+    return cams
+
+
 class MiniCam:
     """Drop-in for gs_renderer.MiniCam (gs_renderer.py:853-879)."""
 

@@ -131,3 +131,17 @@ def test_synthetic_workload_shapes():
     assert len(cams) == 4 and cams[0].world_view_transform.shape == (4, 4)
     assert len(synthetic.vcr_cameras(64, 32, 32)) == 64
     assert len(synthetic.playback_cameras(136, 32, 32)) == 136
+
+
+def test_batched_camera_builder_equals_camera():
+    import math
+    import numpy as np
+    from gaussianip_b200.cameras import Camera, cameras_from_c2w, look_at_c2w, orbit_position
+    c2ws = [look_at_c2w(orbit_position(az, el, d)) for az, el, d in ((10, 5, 1.4), (-100, -20, 1.6), (170, 29, 1.3))]
+    fovys = [0.8, 1.1, 0.7]
+    batch = cameras_from_c2w(c2ws, fovys, 96, 128, device="cpu")
+    for c2w, fovy, b in zip(c2ws, fovys, batch):
+        ref = Camera(c2w, fovy, 96, 128, data_device="cpu")
+        assert b.FoVx == ref.FoVx and b.tanfovx == ref.tanfovx and b.image_width == 128
+        for name in ("world_view_transform", "projection_matrix", "full_proj_transform", "camera_center"):
+            assert torch.equal(getattr(b, name), getattr(ref, name)), name
