@@ -90,6 +90,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 
 constexpr uint32_t ST_AGG = 1u << 30, ST_PREFIX = 2u << 30, ST_MASK = (1u << 30) - 1;
 constexpr int MAX_PASSES = 8;
+// All blocks of a 1-2 M key pass are co-resident (one wave), so the inclusive prefix travels
+// down the chain of blocks one look-back round trip at a time: read LB predecessors per trip.
+constexpr int LB = 4;
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -206,13 +209,16 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
       *mine = ST_AGG | run;
       long long j = (long long)bid - 1;
       bool found = false;
-      while (!found) {                           // four predecessors per round trip
-        uint32_t v[4];
+      while (!found) {                           // LB predecessors per L2 round trip
+        uint32_t v[LB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (j - k >= 0) ? status[(size_t)(j - k) * 256 + tid] : ST_PREFIX;
+        for (int k = 0; k < LB; ++k) {
+          v[k] = 2u << 30;                       // virtual block -1: inclusive prefix 0
+          if (j - k >= 0) v[k] = status[(size_t)(j - k) * 256 + tid];
+        }
         int used = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < LB; ++k) {
           if (found || used != k) continue;
           const uint32_t flag = v[k] & ~ST_MASK;
           if (flag == 0) continue;               // running but not published yet: retry from here
