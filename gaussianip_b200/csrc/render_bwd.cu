@@ -84,7 +84,10 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   const int pix_y = ty * TILE_Y + wy + (lane >> 3);
   const bool inside = pix_x < v.W && pix_y < v.H;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
-  const float cxw = (float)(tx * TILE_X + wx) + 3.5f, cyw = (float)(ty * TILE_Y + wy) + 1.5f;
+  // Cull rectangle of the warp = bounding box of the pixels that have started their walk (a
+  // pixel joins when the position drops to its n_contrib); it grows towards the full 8x4 block.
+  float cxw = 0.f, cyw = 0.f, hwx = -1.f, hwy = -1.f;
+  uint32_t active_prev = 0u;
   const size_t hw = (size_t)v.H * v.W;
   const size_t pix = (size_t)pix_y * v.W + pix_x;
 
@@ -138,10 +141,20 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
     float4 (*st)[32] = ring[c & (STAGES - 1)];
     const int base = (chunks - 1 - c) * 32;
     const int e = base + lane;
+    const bool started = my_last > (uint32_t)base;          // has a position inside or behind this chunk
+    const uint32_t active = __ballot_sync(0xffffffffu, started);
+    if (active != active_prev) {
+      active_prev = active;
+      const int lx = lane & 7, ly = lane >> 3;
+      const int x0 = __reduce_min_sync(0xffffffffu, started ? lx : 64), x1 = __reduce_max_sync(0xffffffffu, started ? lx : -1);
+      const int y0 = __reduce_min_sync(0xffffffffu, started ? ly : 64), y1 = __reduce_max_sync(0xffffffffu, started ? ly : -1);
+      hwx = 0.5f * (float)(x1 - x0); hwy = 0.5f * (float)(y1 - y0);
+      cxw = (float)(tx * TILE_X + wx + x0) + hwx; cyw = (float)(ty * TILE_Y + wy + y0) + hwy;
+    }
     bool hit = false;
     if (e < n) {
       const float4 a = st[0][lane];
-      hit = (fabsf(a.x - cxw) <= a.z + 3.5f) && (fabsf(a.y - cyw) <= a.w + 1.5f);
+      hit = (fabsf(a.x - cxw) <= a.z + hwx) && (fabsf(a.y - cyw) <= a.w + hwy);
     }
     uint32_t mask = __ballot_sync(0xffffffffu, hit);
     // Hits are taken two at a time (back to front): the geometry/alpha of both are independent
@@ -218,6 +231,8 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       } else if (any1) {
         tot1 = butterfly12(g[1], lane);
       }
+      // (direct per-lane atomics for splats that only graze the warp were measured slower:
+      //  521 -> 560 us at FRINGE=3, 569 us at FRINGE=1; the butterfly is kept for every hit)
       if (writer) {
         if (any0 && tot0 != 0.0f)
           atomicAdd(reinterpret_cast<float*>(ggrad + gring[c & (STAGES - 1)][k[0]]) + slot, tot0);

@@ -48,7 +48,12 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   const int pix_y = ty * TILE_Y + wy + (lane >> 3);
   const bool inside = pix_x < v.W && pix_y < v.H;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
-  const float cxw = (float)(tx * TILE_X + wx) + 3.5f, cyw = (float)(ty * TILE_Y + wy) + 1.5f;
+  // Cull rectangle of the warp = bounding box of its pixels that are still accumulating.  It
+  // starts as the whole 8x4 block and shrinks as pixels saturate, so the long-running warps
+  // (a few unsaturated silhouette pixels) stop paying for splats that only reach finished pixels.
+  float cxw = (float)(tx * TILE_X + wx) + 3.5f, cyw = (float)(ty * TILE_Y + wy) + 1.5f;
+  float hwx = 3.5f, hwy = 1.5f;
+  uint32_t alive_prev = 0xffffffffu;
 
   const uint2 range = ranges[tile];
   const int n = (int)(range.y - range.x);
@@ -89,10 +94,19 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       __syncwarp();                              // ... and for every lane of the warp
       float4 (*st)[32] = ring[c & (STAGES - 1)];
       const int e = c * 32 + lane;
+      const uint32_t alive = __ballot_sync(0xffffffffu, !done);
+      if (alive != alive_prev) {
+        alive_prev = alive;
+        const int lx = lane & 7, ly = lane >> 3;
+        const int x0 = __reduce_min_sync(0xffffffffu, done ? 64 : lx), x1 = __reduce_max_sync(0xffffffffu, done ? -1 : lx);
+        const int y0 = __reduce_min_sync(0xffffffffu, done ? 64 : ly), y1 = __reduce_max_sync(0xffffffffu, done ? -1 : ly);
+        hwx = 0.5f * (float)(x1 - x0); hwy = 0.5f * (float)(y1 - y0);
+        cxw = (float)(tx * TILE_X + wx + x0) + hwx; cyw = (float)(ty * TILE_Y + wy + y0) + hwy;
+      }
       bool hit = false;
       if (e < n) {
         const float4 a = st[0][lane];
-        hit = (fabsf(a.x - cxw) <= a.z + 3.5f) && (fabsf(a.y - cyw) <= a.w + 1.5f);
+        hit = (fabsf(a.x - cxw) <= a.z + hwx) && (fabsf(a.y - cyw) <= a.w + hwy);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       // Hits are taken four at a time: the four alphas (LDS, conic, ex2) are independent and
