@@ -48,7 +48,8 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
 
     def compile_one(name: str):
         src = CSRC / name
-        flags = ARCH + COMMON + PER_FILE.get(name, []) + (["-Xptxas", "-v"] if ptxas_info else [])
+        flags = ARCH + COMMON + PER_FILE.get(name, []) + (["-Xptxas", "-v"] if ptxas_info else []) + \
+            os.environ.get("GSB_NVCC_EXTRA", "").split()          # e.g. -DGSB_FWD_STAGES=2 for tuning sweeps
         obj = OBJ / (name + ".o")
         stamp_file = OBJ / (name + ".stamp")
         stamp = _stamp(src, flags)
