@@ -18,7 +18,7 @@ namespace {
 
 constexpr int WARPS = 8;
 #ifndef GSB_BWD_STAGES
-#define GSB_BWD_STAGES 4
+#define GSB_BWD_STAGES 2
 #endif
 constexpr int STAGES = GSB_BWD_STAGES;
 

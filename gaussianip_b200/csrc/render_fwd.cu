@@ -8,8 +8,12 @@
 // blend.  Lane l first tests whether instance l of the chunk can reach any of the warp's 32
 // pixels (conservative extent test, see preprocess.cu); the ballot gives the hit list and only
 // hits are evaluated, in list order, so results are identical to evaluating everything.  A
-// warp stops as soon as all of its pixels are saturated.  (r1a profile of the block-synchronous
-// version: 44 % of issue stalls were CTA barriers — warps waiting for the busiest sibling.)
+// warp stops as soon as all of its pixels are saturated.
+// Measured alternatives (profiles/r1_experiments.md): block-synchronous 256-instance batches lost
+// 44 % of issue slots to CTA barriers (r1a); deeper private rings are SLOWER (4 stages 241 us, 8
+// stages 318 us vs 232 us at 2: shared memory is taken from L1, which serves the 8 warps' re-reads
+// of the same records); one producer warp feeding a ring shared by the 8 consumers was slower too
+// (257-297 us: a single warp's gather latency cannot feed eight consumers).
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -19,7 +23,7 @@ namespace {
 constexpr int WARPS = 8;
 constexpr int HB = 4;          // hits evaluated together (ILP)
 #ifndef GSB_FWD_STAGES
-#define GSB_FWD_STAGES 4
+#define GSB_FWD_STAGES 2
 #endif
 constexpr int STAGES = GSB_FWD_STAGES;   // chunks in flight per warp (power of two)
 
