@@ -329,24 +329,46 @@ emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ ord
     mine += cnt[k];
   }
   uint32_t off = blocksums[blockIdx.x] + block_exclusive_scan_256(mine, s_warp, nullptr);
+  constexpr uint32_t BIG = 64;   // splats touching more tiles than this are emitted by the whole warp
+  uint32_t offk[SC_IPT];
+#pragma unroll
+  for (int k = 0; k < SC_IPT; ++k) { offk[k] = off; off += cnt[k]; }
+  auto put = [&](long long o, uint32_t tile, uint32_t dk, uint32_t g) {
+    if (o < D_cap) {
+      if (MODE == 0) tkeys[o] = tile;
+      else keys64[o] = ((uint64_t)tile << 32) | dk;
+      vals[o] = g;
+    }
+  };
 #pragma unroll
   for (int k = 0; k < SC_IPT; ++k) {
-    if (cnt[k] == 0) continue;
+    if (cnt[k] == 0 || cnt[k] > BIG) continue;
     const ushort4 rc = rect[gid[k]];
     const uint32_t dk = (MODE == 1) ? dkeys[gid[k]] : 0u;
-    long long o = off;
-    for (int y = rc.y; y < rc.w; ++y) {
-      for (int x = rc.x; x < rc.z; ++x) {
-        if (o < D_cap) {
-          const uint32_t tile = (uint32_t)(y * gx + x);
-          if (MODE == 0) tkeys[o] = tile;
-          else keys64[o] = ((uint64_t)tile << 32) | dk;
-          vals[o] = gid[k];
-        }
-        ++o;
+    long long o = offk[k];
+    for (int y = rc.y; y < rc.w; ++y)
+      for (int x = rc.x; x < rc.z; ++x) put(o++, (uint32_t)(y * gx + x), dk, gid[k]);
+  }
+  // large splats (a Gaussian in front of a zoomed-in camera can touch every tile): one lane looping
+  // over thousands of tiles would serialise the warp, so the 32 lanes share each of them
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; ++k) {
+    uint32_t big = __ballot_sync(0xffffffffu, cnt[k] > BIG);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const uint32_t g = __shfl_sync(0xffffffffu, gid[k], src);
+      const uint32_t c = __shfl_sync(0xffffffffu, cnt[k], src);
+      const uint32_t o0 = __shfl_sync(0xffffffffu, offk[k], src);
+      const ushort4 rc = rect[g];
+      const uint32_t dk = (MODE == 1) ? dkeys[g] : 0u;
+      const uint32_t wx = (uint32_t)(rc.z - rc.x);
+      for (uint32_t i = lane; i < c; i += 32) {
+        const uint32_t y = rc.y + i / wx, x = rc.x + i % wx;
+        put((long long)o0 + i, y * (uint32_t)gx + x, dk, g);
       }
     }
-    off += cnt[k];
   }
 }
 

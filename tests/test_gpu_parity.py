@@ -48,6 +48,8 @@ SCENES = {
     "precomp_color_cov": dict(P=2000, H=96, W=96, sh_degree=0, precomp_color=True, precomp_cov=True),
     "scale_modifier": dict(P=2000, H=96, W=96, sh_degree=2, scale_modifier=1.7),
     # several thousand instances per tile (long per-warp walks, many ring refills)
+    # splats that cover most of the image: hundreds of tiles per Gaussian (warp-cooperative emission)
+    "huge_splats": dict(P=300, H=256, W=256, sh_degree=0, scale_boost=60.0),
     "dense_long_lists": dict(P=12000, H=64, W=64, sh_degree=0, scale_boost=3.0, bg=(0.2, 0.1, 0.4)),
 }
 
