@@ -172,7 +172,7 @@ int gsb_preprocess_fwd(const GsbSettings* s, int P, int K, const float* means3D,
                                cov3D_precomp, radii_out, at<Geom>(saved, L.off_geom),
                                at<uint8_t>(saved, L.off_clamped), at<ushort4>(scratch, L.off_rect),
                                at<uint32_t>(scratch, L.off_tiles), at<uint32_t>(scratch, L.off_dkeys0),
-                               at<uint32_t>(saved, L.off_counts), s->debug != 0, (cudaStream_t)stream);
+                               at<char>(scratch, L.off_hist), s->debug != 0, (cudaStream_t)stream);
 }
 
 int gsb_bin_sort(const GsbSettings* s, int P, void* saved, void* scratch, long long D_cap, int mode,
@@ -328,9 +328,9 @@ static int radix_entry(long long n, const void* keys_in, const uint32_t* vals_in
   }
   if (key_bytes == 4)
     return radix_sort_pairs<uint32_t>(n, nullptr, (const uint32_t*)keys_in, vals_in, (uint32_t*)kA, vA,
-                                      (uint32_t*)kB, vB, end_bit, false, hist, false, st);
+                                      (uint32_t*)kB, vB, end_bit, false, false, hist, false, st);
   return radix_sort_pairs<uint64_t>(n, nullptr, (const uint64_t*)keys_in, vals_in, (uint64_t*)kA, vA,
-                                    (uint64_t*)kB, vB, end_bit, false, hist, false, st);
+                                    (uint64_t*)kB, vB, end_bit, false, false, hist, false, st);
 }
 
 int gsb_radix_sort_pairs_u32(long long n, const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,

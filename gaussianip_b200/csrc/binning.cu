@@ -132,7 +132,7 @@ radix_global_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restri
 
 template <typename KeyT>
 constexpr size_t onesweep_smem_bytes() {
-  return (size_t)RS_TILE * (sizeof(KeyT) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + RS_WARPS + 4) * sizeof(uint32_t);
+  return (size_t)RS_TILE * (sizeof(KeyT) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + RS_WARPS + 4 + 256) * sizeof(uint32_t);
 }
 
 template <typename KeyT, bool IOTA>
@@ -141,6 +141,7 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                       const uint32_t* __restrict__ d_n, long long n_cap, int shift,
                       const uint32_t* __restrict__ ghist /*[256] of this pass*/,
+                      uint32_t* __restrict__ ghist_next /*[256] of the next pass, or null*/,
                       volatile uint32_t* __restrict__ status /*[num_blocks][256] of this pass*/,
                       uint32_t* __restrict__ block_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -150,10 +151,12 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
   uint32_t* s_goff = reinterpret_cast<uint32_t*>(s_cnt + RS_WARPS);         // global slot - local slot, per digit
   uint32_t* s_warp = s_goff + 256;
   uint32_t* s_bid = s_warp + RS_WARPS;
+  uint32_t* s_hn = s_bid + 4;                                               // next pass's digit counts
 
   const long long n = load_n(d_n, n_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *s_bid = atomicAdd(block_counter, 1u);
+  s_hn[tid] = 0;
 #pragma unroll
   for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][tid] = 0;
   // exclusive scan of the global histogram = first output slot of every digit
@@ -174,6 +177,13 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
     const bool valid = idx < n;
     key[r] = valid ? keys_in[idx] : (KeyT)0;
     val[r] = valid ? (IOTA ? (uint32_t)idx : vals_in[idx]) : 0u;
+  }
+  if (ghist_next) {
+    // the histogram of the NEXT digit does not depend on the arrangement: count it here, while
+    // the keys are in registers, instead of in a separate pass over the keys
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r)
+      if (seg + r * 32 + lane < n) atomicAdd(&s_hn[digit_of(key[r], shift + 8)], 1u);
   }
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
@@ -255,6 +265,7 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
     keys_out[pos] = k;
     vals_out[pos] = s_vals[i];
   }
+  if (ghist_next && s_hn[tid]) atomicAdd(&ghist_next[tid], s_hn[tid]);   // ordered by the barrier above
 }
 
 // ---- scan of tiles_touched (gathered through an order) + instance emission -------------------
@@ -312,8 +323,11 @@ __global__ void __launch_bounds__(RS_THREADS)
 emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order, int P,
             const uint32_t* __restrict__ blocksums, const ushort4* __restrict__ rect,
             const uint32_t* __restrict__ dkeys, int gx, long long D_cap, uint32_t* __restrict__ tkeys,
-            uint64_t* __restrict__ keys64, uint32_t* __restrict__ vals) {
+            uint64_t* __restrict__ keys64, uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist0) {
   __shared__ uint32_t s_warp[RS_WARPS];
+  __shared__ uint32_t s_h0[256];     // digit-0 histogram of the emitted keys (first pass of the sort)
+  s_h0[threadIdx.x] = 0;
+  __syncthreads();
   // blocked arrangement: thread t owns SC_IPT consecutive Gaussians of the emission order
   const int first = blockIdx.x * SC_TILE + threadIdx.x * SC_IPT;
   uint32_t gid[SC_IPT], cnt[SC_IPT];
@@ -338,6 +352,7 @@ emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ ord
       if (MODE == 0) tkeys[o] = tile;
       else keys64[o] = ((uint64_t)tile << 32) | dk;
       vals[o] = g;
+      atomicAdd(&s_h0[(MODE == 0 ? tile : dk) & 0xFFu], 1u);
     }
   };
 #pragma unroll
@@ -370,6 +385,8 @@ emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ ord
       }
     }
   }
+  __syncthreads();
+  if (s_h0[threadIdx.x]) atomicAdd(&ghist0[threadIdx.x], s_h0[threadIdx.x]);
 }
 
 template <typename KeyT>
@@ -438,13 +455,31 @@ size_t radix_tmp_bytes(long long n_cap) {
   return (size_t)(MAX_PASSES * 256 + 256 + (size_t)MAX_PASSES * (nb > 0 ? nb : 1) * 256) * sizeof(uint32_t);
 }
 
+static size_t radix_used_bytes(long long n_cap, int passes) {
+  const long long nb = (n_cap + RS_TILE - 1) / RS_TILE;
+  return (size_t)(MAX_PASSES * 256 + 256 + (size_t)passes * (nb > 0 ? nb : 1) * 256) * sizeof(uint32_t);
+}
+
+// Zero the histograms / counters / look-back words of one sort.  Must run BEFORE the kernel that
+// produces the digit-0 histogram (preprocess for the depth keys, emit for the tile keys).
+int radix_prepare(long long n_cap, int end_bit, void* tmp, cudaStream_t st) {
+  if (n_cap <= 0) return GSB_OK;
+  GSB_CUDA(cudaMemsetAsync(tmp, 0, radix_used_bytes(n_cap, radix_num_passes(end_bit)), st));
+  return GSB_OK;
+}
+
+uint32_t* radix_hist0(void* tmp) { return static_cast<uint32_t*>(tmp); }
+
 // Stable LSD sort on bits [0,end_bit).  Pass 0 reads (src_keys, src_vals); pass p writes
 // buffer A when p is even and buffer B when p is odd.  src may alias B (never A).  The result
 // is in A when the number of passes is odd, in B when it is even (see radix_result_in_A).
+// hist0_ready: the caller ran radix_prepare and the producer of the keys already accumulated the
+// digit-0 histogram into radix_hist0(tmp); otherwise both happen here.  Every pass counts the next
+// pass's digits while it holds the keys, so there is no separate histogram pass.
 template <typename KeyT>
 int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys, const uint32_t* src_vals,
                      KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
-                     bool iota_vals, void* tmp, bool debug, cudaStream_t st) {
+                     bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st) {
   if (n_cap <= 0) return GSB_OK;
   const int passes = radix_num_passes(end_bit);
   if (passes == 0) return GSB_OK;
@@ -453,8 +488,6 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
   uint32_t* ghist = static_cast<uint32_t*>(tmp);
   uint32_t* counters = ghist + MAX_PASSES * 256;
   uint32_t* status = counters + 256;
-  const size_t used = (size_t)(MAX_PASSES * 256 + 256 + (size_t)passes * nb * 256) * sizeof(uint32_t);
-  GSB_CUDA(cudaMemsetAsync(tmp, 0, used, st));
   constexpr size_t smem = onesweep_smem_bytes<KeyT>();
   {
     static bool configured[64] = {};   // the attribute is per device and per instantiation
@@ -468,29 +501,34 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
       configured[dev & 63] = true;
     }
   }
-  radix_global_hist_kernel<KeyT><<<nb, RS_THREADS, 0, st>>>(src_keys, d_n, n_cap, passes, ghist);
-  GSB_POST_LAUNCH(debug, st, "radix_global_hist_kernel");
+  if (!hist0_ready) {
+    int rc = radix_prepare(n_cap, end_bit, tmp, st);
+    if (rc) return rc;
+    radix_global_hist_kernel<KeyT><<<nb, RS_THREADS, 0, st>>>(src_keys, d_n, n_cap, 1, ghist);
+    GSB_POST_LAUNCH(debug, st, "radix_global_hist_kernel");
+  }
   for (int p = 0; p < passes; ++p) {
     const KeyT* kin = p == 0 ? src_keys : ((p & 1) ? keysA : keysB);
     const uint32_t* vin = p == 0 ? src_vals : ((p & 1) ? valsA : valsB);
     KeyT* kout = (p & 1) ? keysB : keysA;
     uint32_t* vout = (p & 1) ? valsB : valsA;
     uint32_t* stp = status + (size_t)p * nb * 256;
+    uint32_t* gnext = p + 1 < passes ? ghist + (p + 1) * 256 : nullptr;
     if (p == 0 && iota_vals)
       radix_onesweep_kernel<KeyT, true><<<nb, RS_THREADS, smem, st>>>(kin, vin, kout, vout, d_n, n_cap, 8 * p,
-                                                                      ghist + p * 256, stp, counters + p);
+                                                                      ghist + p * 256, gnext, stp, counters + p);
     else
       radix_onesweep_kernel<KeyT, false><<<nb, RS_THREADS, smem, st>>>(kin, vin, kout, vout, d_n, n_cap, 8 * p,
-                                                                       ghist + p * 256, stp, counters + p);
+                                                                       ghist + p * 256, gnext, stp, counters + p);
     GSB_POST_LAUNCH(debug, st, "radix_onesweep_kernel");
   }
   return GSB_OK;
 }
 
 template int radix_sort_pairs<uint32_t>(long long, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*,
-                                        uint32_t*, uint32_t*, uint32_t*, int, bool, void*, bool, cudaStream_t);
+                                        uint32_t*, uint32_t*, uint32_t*, int, bool, bool, void*, bool, cudaStream_t);
 template int radix_sort_pairs<uint64_t>(long long, const uint32_t*, const uint64_t*, const uint32_t*, uint64_t*,
-                                        uint32_t*, uint64_t*, uint32_t*, int, bool, void*, bool, cudaStream_t);
+                                        uint32_t*, uint64_t*, uint32_t*, int, bool, bool, void*, bool, cudaStream_t);
 
 int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbLayout& L,
                     long long D_cap, int mode, uint32_t* host_counts, cudaEvent_t event, bool debug,
@@ -530,7 +568,8 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     uint32_t* kB = at<uint32_t>(scratch, L.off_dkeys2);
     uint32_t* vB = at<uint32_t>(scratch, L.off_didx1);
     prof_begin(GSB_STAGE_DEPTH_SORT, st);
-    rc = radix_sort_pairs<uint32_t>(P, nullptr, dkeys, nullptr, kA, vA, kB, vB, 32, true, hist, debug, st);
+    // digit-0 histogram of the depth keys was accumulated by preprocess_fwd (after radix_prepare)
+    rc = radix_sort_pairs<uint32_t>(P, nullptr, dkeys, nullptr, kA, vA, kB, vB, 32, true, true, hist, debug, st);
     prof_end(GSB_STAGE_DEPTH_SORT, st);
     if (rc) return rc;
     prof_begin(GSB_STAGE_SCAN_EMIT, st);
@@ -547,13 +586,14 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     uint32_t* tkB = at<uint32_t>(scratch, L.off_tkeys1);
     uint32_t* tvA = inA ? point_list : alt_vals;
     uint32_t* tvB = inA ? alt_vals : point_list;
+    if ((rc = radix_prepare(D_cap, tile_bits, hist, st))) return rc;
     emit_kernel<0><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums, rect, dkeys, v.gx, D_cap, tkB,
-                                                     nullptr, tvB);
+                                                     nullptr, tvB, radix_hist0(hist));
     GSB_POST_LAUNCH(debug, st, "emit_kernel");
     prof_end(GSB_STAGE_SCAN_EMIT, st);
     prof_begin(GSB_STAGE_TILE_SORT, st);
-    rc = radix_sort_pairs<uint32_t>(D_cap, counts + CNT_D, tkB, tvB, tkA, tvA, tkB, tvB, tile_bits, false, hist,
-                                    debug, st);
+    rc = radix_sort_pairs<uint32_t>(D_cap, counts + CNT_D, tkB, tvB, tkA, tvA, tkB, tvB, tile_bits, false, true,
+                                    hist, debug, st);
     prof_end(GSB_STAGE_TILE_SORT, st);
     if (rc) return rc;
     ProfScope pr(GSB_STAGE_RANGES, st);
@@ -577,13 +617,14 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     uint64_t* kB = at<uint64_t>(scratch, L.off_keys64_1);
     uint32_t* tvA = inA ? point_list : alt_vals;
     uint32_t* tvB = inA ? alt_vals : point_list;
+    if ((rc = radix_prepare(D_cap, end_bit, hist, st))) return rc;
     emit_kernel<1><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums, rect, dkeys, v.gx, D_cap,
-                                                     nullptr, kB, tvB);
+                                                     nullptr, kB, tvB, radix_hist0(hist));
     GSB_POST_LAUNCH(debug, st, "emit_kernel");
     prof_end(GSB_STAGE_SCAN_EMIT, st);
     prof_begin(GSB_STAGE_TILE_SORT, st);
-    rc = radix_sort_pairs<uint64_t>(D_cap, counts + CNT_D, kB, tvB, kA, tvA, kB, tvB, end_bit, false, hist, debug,
-                                    st);
+    rc = radix_sort_pairs<uint64_t>(D_cap, counts + CNT_D, kB, tvB, kA, tvA, kB, tvB, end_bit, false, true, hist,
+                                    debug, st);
     prof_end(GSB_STAGE_TILE_SORT, st);
     if (rc) return rc;
     ProfScope pr(GSB_STAGE_RANGES, st);

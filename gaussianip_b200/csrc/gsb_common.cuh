@@ -95,7 +95,7 @@ int launch_preprocess_fwd(const View& v, int P, int K, const float* means3D, con
                           const float* rots, const float* opac, const float* shs,
                           const float* colors, const float* cov3D, int32_t* radii, Geom* geom,
                           uint8_t* clamped, ushort4* rect, uint32_t* tiles, uint32_t* dkeys,
-                          uint32_t* counts, bool debug, cudaStream_t st);
+                          void* radix_tmp, bool debug, cudaStream_t st);
 
 int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbLayout& L,
                     long long D_cap, int mode, uint32_t* host_counts, cudaEvent_t event, bool debug,
@@ -123,7 +123,9 @@ size_t radix_tmp_bytes(long long n_cap);
 template <typename KeyT>
 int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys, const uint32_t* src_vals,
                      KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
-                     bool iota_vals, void* tmp, bool debug, cudaStream_t st);
+                     bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st);
+int radix_prepare(long long n_cap, int end_bit, void* tmp, cudaStream_t st);
+uint32_t* radix_hist0(void* tmp);
 bool radix_result_in_A(int passes);
 int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void* scratch, const GsbLayout& L,
                              long long D_cap, uint64_t* keys_out, cudaStream_t st);

@@ -12,6 +12,8 @@ namespace gsb {
 
 namespace {
 
+constexpr int PRE_IPT = 4;
+
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // SH -> RGB, term order of gaussiansplatting/utils/sh_utils.py:57-99.  sh points at this
@@ -45,21 +47,13 @@ __device__ __forceinline__ float sh_channel(int deg, const float* __restrict__ s
   return r;
 }
 
-__global__ void __launch_bounds__(256)
-preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
-                      const float* __restrict__ scales, const float* __restrict__ rots,
-                      const float* __restrict__ opac, const float* __restrict__ shs,
-                      const float* __restrict__ colors, const float* __restrict__ cov3Dp,
-                      int32_t* __restrict__ radii, Geom* __restrict__ geom,
-                      uint8_t* __restrict__ clamped, ushort4* __restrict__ rect,
-                      uint32_t* __restrict__ tiles, uint32_t* __restrict__ dkeys) {
-  __shared__ float sV[16], sM[16], sCam[3];
-  if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sM[threadIdx.x] = v.proj[threadIdx.x]; }
-  if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-
+__device__ __forceinline__ void
+preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, const float* sCam,
+               const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rots,
+               const float* __restrict__ opac, const float* __restrict__ shs, const float* __restrict__ colors,
+               const float* __restrict__ cov3Dp, int32_t* __restrict__ radii, Geom* __restrict__ geom,
+               uint8_t* __restrict__ clamped, ushort4* __restrict__ rect, uint32_t* __restrict__ tiles,
+               uint32_t* __restrict__ dkeys, uint32_t* s_h0) {
   const float px = means3D[3 * i], py = means3D[3 * i + 1], pz = means3D[3 * i + 2];
   const float tx = ((sV[0] * px + sV[4] * py) + sV[8] * pz) + sV[12];
   const float ty = ((sV[1] * px + sV[5] * py) + sV[9] * pz) + sV[13];
@@ -181,7 +175,39 @@ preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
   }
   radii[i] = visible ? rad : 0;
   tiles[i] = visible ? ntiles : 0u;
-  dkeys[i] = visible ? __float_as_uint(tz) : 0xFFFFFFFFu;
+  const uint32_t dk = visible ? __float_as_uint(tz) : 0xFFFFFFFFu;
+  dkeys[i] = dk;
+  // culled Gaussians all carry key 0xFFFFFFFF: aggregate them per warp before touching the counter
+  const uint32_t culled = __ballot_sync(__activemask(), !visible);
+  if (visible) atomicAdd(&s_h0[dk & 0xFFu], 1u);
+  else if ((threadIdx.x & 31) == __ffs(culled) - 1) atomicAdd(&s_h0[255], (uint32_t)__popc(culled));
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
+                      const float* __restrict__ scales, const float* __restrict__ rots,
+                      const float* __restrict__ opac, const float* __restrict__ shs,
+                      const float* __restrict__ colors, const float* __restrict__ cov3Dp,
+                      int32_t* __restrict__ radii, Geom* __restrict__ geom,
+                      uint8_t* __restrict__ clamped, ushort4* __restrict__ rect,
+                      uint32_t* __restrict__ tiles, uint32_t* __restrict__ dkeys,
+                      uint32_t* __restrict__ ghist0) {
+  __shared__ float sV[16], sM[16], sCam[3];
+  __shared__ uint32_t s_h0[256];   // digit-0 histogram of the depth keys (first pass of the depth sort)
+  s_h0[threadIdx.x] = 0;
+  if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sM[threadIdx.x] = v.proj[threadIdx.x]; }
+  if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  __syncthreads();
+  // PRE_IPT Gaussians per thread: 4x fewer CTAs flushing their 256-bin histogram to the same
+  // 256 global counters (one flush per 256 Gaussians cost +22 us of same-address L2 atomics)
+#pragma unroll 1
+  for (int k = 0; k < PRE_IPT; ++k) {
+    const int i = (blockIdx.x * PRE_IPT + k) * 256 + threadIdx.x;
+    if (i < P) preprocess_one(v, i, K, sV, sM, sCam, means3D, scales, rots, opac, shs, colors, cov3Dp, radii, geom,
+                              clamped, rect, tiles, dkeys, s_h0);
+  }
+  __syncthreads();
+  if (s_h0[threadIdx.x]) atomicAdd(&ghist0[threadIdx.x], s_h0[threadIdx.x]);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -199,12 +225,14 @@ int launch_preprocess_fwd(const View& v, int P, int K, const float* means3D, con
                           const float* rots, const float* opac, const float* shs,
                           const float* colors, const float* cov3D, int32_t* radii, Geom* geom,
                           uint8_t* clamped, ushort4* rect, uint32_t* tiles, uint32_t* dkeys,
-                          uint32_t* counts, bool debug, cudaStream_t st) {
-  (void)counts;
+                          void* radix_tmp, bool debug, cudaStream_t st) {
   if (P == 0) return GSB_OK;
-  const int grid = (P + 255) / 256;
+  const int grid = (P + 256 * PRE_IPT - 1) / (256 * PRE_IPT);
+  // the kernel also accumulates the digit-0 histogram of the depth keys for the depth sort
+  int rc = radix_prepare(P, 32, radix_tmp, st);
+  if (rc) return rc;
   preprocess_fwd_kernel<<<grid, 256, 0, st>>>(v, P, K, means3D, scales, rots, opac, shs, colors, cov3D,
-                                              radii, geom, clamped, rect, tiles, dkeys);
+                                              radii, geom, clamped, rect, tiles, dkeys, radix_hist0(radix_tmp));
   GSB_POST_LAUNCH(debug, st, "preprocess_fwd_kernel");
   return GSB_OK;
 }
