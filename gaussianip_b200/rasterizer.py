@@ -167,49 +167,97 @@ class _Saved:
         return out[:self.num_rendered]
 
 
-def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):
-    lib = _lib.load()
-    device = means3D.device
-    if device.type != "cuda":
-        raise ValueError("gaussianip_b200 runs on CUDA tensors only (no CPU fallback)")
-    P = means3D.shape[0]
-    H, W = int(rs.image_height), int(rs.image_width)
-    K = shs.shape[1] if shs is not None else 0
-    with torch.cuda.device(device):
-        ws = _workspace(device)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        s, keep = _make_settings(rs, device)
-        if out is not None:
-            color, radii, depth, alpha = out           # caller-owned contiguous slices
-        else:
-            color = torch.empty(3, H, W, dtype=torch.float32, device=device)
-            depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
-            alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
-            radii = torch.empty(P, dtype=torch.int32, device=device)
-        while True:
-            d_cap = ws.capacity_for(P)
-            L = _lib.layout(P, H, W, d_cap)
-            scratch = ws.ensure_scratch(L.scratch_bytes)
-            block = torch.empty(L.saved_bytes, dtype=torch.uint8, device=device)
-            rc = lib.gsb_forward(C.byref(s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(opacities),
-                                 _ptr(shs), _ptr(colors), _ptr(cov3D), radii.data_ptr(), color.data_ptr(),
-                                 depth.data_ptr(), alpha.data_ptr(), block.data_ptr(), scratch.data_ptr(), d_cap,
-                                 ws.binning_mode, ws.host_counts.data_ptr(), ws.event.cuda_event, stream)
+class _ForwardCall:
+    """One view's forward: enqueue() queues every kernel on the CURRENT stream; finish() waits for
+    the 32-byte counts copy and, if D exceeded the instance capacity, re-enqueues with a larger
+    workspace (nothing can have observed the outputs yet)."""
+
+    def __init__(self, rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):
+        self.args = (means3D, shs, colors, opacities, scales, rotations, cov3D)
+        device = means3D.device
+        if device.type != "cuda":
+            raise ValueError("gaussianip_b200 runs on CUDA tensors only (no CPU fallback)")
+        self.device = device
+        self.P = means3D.shape[0]
+        self.H, self.W = int(rs.image_height), int(rs.image_width)
+        self.K = shs.shape[1] if shs is not None else 0
+        self.rs = rs
+        self.out = out
+        self.stream = None
+
+    def enqueue(self):
+        lib = _lib.load()
+        means3D, shs, colors, opacities, scales, rotations, cov3D = self.args
+        device, P, H, W, K = self.device, self.P, self.H, self.W, self.K
+        with torch.cuda.device(device):
+            if self.stream is None:
+                self.stream = torch.cuda.current_stream(device)
+                self.ws = _workspace(device)
+                self.s, self.keep = _make_settings(self.rs, device)
+                if self.out is not None:
+                    self.color, self.radii, self.depth, self.alpha = self.out   # caller-owned contiguous slices
+                else:
+                    self.color = torch.empty(3, H, W, dtype=torch.float32, device=device)
+                    self.depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
+                    self.alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
+                    self.radii = torch.empty(P, dtype=torch.int32, device=device)
+            ws = self.ws
+            self.d_cap = ws.capacity_for(P)
+            self.L = _lib.layout(P, H, W, self.d_cap)
+            self.scratch = ws.ensure_scratch(self.L.scratch_bytes)
+            self.block = torch.empty(self.L.saved_bytes, dtype=torch.uint8, device=device)
+            rc = lib.gsb_forward(C.byref(self.s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
+                                 _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), self.radii.data_ptr(),
+                                 self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
+                                 self.block.data_ptr(), self.scratch.data_ptr(), self.d_cap, ws.binning_mode,
+                                 ws.host_counts.data_ptr(), ws.event.cuda_event, self.stream.cuda_stream)
             _lib.check(rc, "gsb_forward")
+        return self
+
+    def finish(self):
+        ws, P = self.ws, self.P
+        while True:
             ws.event.synchronize()          # waits for the 32-byte counts copy only
             D = int(ws.host_counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
-            if D <= d_cap:
+            if D <= self.d_cap:
                 break
             ws.d_cap = int(D * 1.25) + 4096   # outputs were not observable yet: enqueue again, larger
             ws.retries += 1
+            with torch.cuda.stream(self.stream):
+                self.enqueue()
         ws.last_num_rendered = D
         # follow the scene downwards slowly so one huge view does not pin memory forever
         if D * 4 < ws.d_cap and ws.d_cap > max(1 << 16, 4 * P):
             ws.d_cap = max(1 << 16, 4 * P, 2 * D)
-    sv = _Saved()
-    sv.block, sv.layout, sv.d_cap, sv.P, sv.K, sv.H, sv.W = block, L, d_cap, P, K, H, W
-    sv.num_rendered, sv.scratch, sv.settings_keep = D, scratch, keep
-    return color, radii, depth, alpha, sv
+        sv = _Saved()
+        sv.block, sv.layout, sv.d_cap, sv.P, sv.K, sv.H, sv.W = self.block, self.L, self.d_cap, P, self.K, self.H, self.W
+        sv.num_rendered, sv.scratch, sv.settings_keep = D, self.scratch, self.keep
+        return self.color, self.radii, self.depth, self.alpha, sv
+
+
+def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):
+    return _ForwardCall(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out).enqueue().finish()
+
+
+# Side streams for the batched multi-view entry: the binning stages of a 1-2 M instance view are
+# latency-bound (one wave of blocks per radix pass), so the views of a step run on separate
+# streams and one view's sort overlaps another view's blend.
+_side_streams = {}
+_multistream = True
+
+
+def set_multistream(enabled: bool) -> None:
+    """Run the views of rasterize_views on separate CUDA streams (default) or back to back."""
+    global _multistream
+    _multistream = bool(enabled)
+
+
+def _streams_for(device: torch.device, n: int):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _side_streams.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
 
 
 def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
@@ -247,6 +295,68 @@ def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rota
                               _ptr(out["rotations"]), _ptr(out["cov3D"]), int(bool(accumulate)), stream)
         _lib.check(rc, "gsb_backward")
         del keep
+    return out
+
+
+def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
+                    g_color, g_depth, g_alpha):
+    """Backward of V views: the blend backward of view v runs on side stream v (they overlap);
+    the per-Gaussian stage runs view after view on the calling stream because it accumulates
+    (beta = 1) into one set of gradient tensors."""
+    lib = _lib.load()
+    device = means3D.device
+    V = len(settings_list)
+    P, K, H, W = svs[0].P, svs[0].K, svs[0].H, svs[0].W
+    with torch.cuda.device(device):
+        main = torch.cuda.current_stream(device)
+        e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=device)
+        out = {"means3D": e(P, 3), "means2D": e(P, 3), "opacities": e(P, 1),
+               "shs": e(P, K, 3) if shs is not None else None, "colors": e(P, 3) if colors is not None else None,
+               "scales": e(P, 3) if scales is not None else None,
+               "rotations": e(P, 4) if rotations is not None else None,
+               "cov3D": e(P, 6) if cov3D is not None else None}
+
+        def grad_in(g, shape):
+            if g is None:
+                return torch.zeros(shape, dtype=torch.float32, device=device)
+            return g.to(dtype=torch.float32).contiguous()
+
+        g_color, g_depth, g_alpha = grad_in(g_color, (V, 3, H, W)), grad_in(g_depth, (V, 1, H, W)), \
+            grad_in(g_alpha, (V, 1, H, W))
+        streams = _streams_for(device, V)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        staged = []
+        for v, (rs, sv, st) in enumerate(zip(settings_list, svs, streams)):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                ws = _workspace(device)
+                s, keep = _make_settings(rs, device)
+                scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
+                rc = lib.gsb_render_bwd(C.byref(s), P, sv.block.data_ptr(), scratch.data_ptr(), sv.d_cap,
+                                        g_color[v].data_ptr(), g_depth[v].data_ptr(), g_alpha[v].data_ptr(),
+                                        st.cuda_stream)
+                _lib.check(rc, "gsb_render_bwd")
+                done = torch.cuda.Event()
+                done.record(st)
+            staged.append((s, keep, scratch, done))
+        for v, (rs, sv) in enumerate(zip(settings_list, svs)):
+            s, keep, scratch, done = staged[v]
+            main.wait_event(done)
+            sv.block.record_stream(main)
+            rc = lib.gsb_preprocess_bwd(C.byref(s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
+                                        _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), radii[v].data_ptr(),
+                                        sv.block.data_ptr(), scratch.data_ptr(), sv.d_cap, _ptr(out["means3D"]),
+                                        _ptr(out["means2D"]), _ptr(out["shs"]), _ptr(out["colors"]),
+                                        _ptr(out["opacities"]), _ptr(out["scales"]), _ptr(out["rotations"]),
+                                        _ptr(out["cov3D"]), int(v > 0), main.cuda_stream)
+            _lib.check(rc, "gsb_preprocess_bwd")
+        # the side streams' scratch blocks are read by the calling stream above; they are persistent
+        # per-(device, stream) workspaces, so no allocator hand-over is involved
+        for st in streams[:V]:
+            back = torch.cuda.Event()
+            back.record(main)
+            st.wait_event(back)              # next use of a side workspace is ordered after these reads
     return out
 
 
@@ -339,10 +449,28 @@ class _RasterizeViews(torch.autograd.Function):
         alpha = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
         radii = torch.empty(V, P, dtype=torch.int32, device=dev)
         svs = []
-        for v, rs in enumerate(settings_list):
-            _, _, _, _, sv = _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
-                                           cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]))
-            svs.append(sv)
+        ctx.multistream = _multistream and V > 1
+        if ctx.multistream:
+            main = torch.cuda.current_stream(dev)
+            streams = _streams_for(dev, V)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            calls = []
+            for v, (rs, st) in enumerate(zip(settings_list, streams)):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    calls.append(_ForwardCall(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
+                                              cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v])).enqueue())
+            for call, st in zip(calls, streams):
+                svs.append(call.finish()[4])
+                join = torch.cuda.Event()
+                join.record(st)
+                main.wait_event(join)
+        else:
+            for v, rs in enumerate(settings_list):
+                _, _, _, _, sv = _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
+                                               cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]))
+                svs.append(sv)
         ctx.settings_list, ctx.svs = list(settings_list), svs
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,
                        cov3Ds_precomp is not None)
@@ -358,6 +486,14 @@ class _RasterizeViews(torch.autograd.Function):
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         means3D, sh, colors, opacities, scales, rotations, cov3D, radii = ctx.saved_tensors
         has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
+        if ctx.multistream:
+            out = _backward_views(ctx.settings_list, ctx.svs, means3D, sh if has_sh else None,
+                                  colors if has_col else None, opacities, scales if has_sc else None,
+                                  rotations if has_rot else None, cov3D if has_cov else None, radii,
+                                  grad_color, grad_depth, grad_alpha)
+            ctx.svs = None
+            return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
+                    out["rotations"], out["cov3D"], None)
         out = None
         for v, (rs, sv) in enumerate(zip(ctx.settings_list, ctx.svs)):
             out = _backward_impl(rs, sv, means3D, sh if has_sh else None, colors if has_col else None, opacities,

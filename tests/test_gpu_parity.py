@@ -281,3 +281,36 @@ def test_batched_views_equal_per_view_calls(cuda_device):
     ((color * wc).sum() + (depth * wd).sum() + (alpha * wa).sum()).backward()
     for k in ("means3D", "means2D", "shs", "opacities", "scales", "rotations"):
         _grad_close(k, b[k].grad, a[k].grad, rtol=2e-5)
+
+
+def test_multistream_equals_single_stream(cuda_device):
+    """The views of rasterize_views on separate streams give the same images and (up to atomic
+    order) the same gradients as back-to-back execution."""
+    from gaussianip_b200 import rasterizer as R, synthetic
+    dev = cuda_device
+    H = W = 128
+    scene = util.humanoid_scene(P=6000, H=H, W=W, sh_degree=2)
+    cams = synthetic.ahds_cameras(4, H, W, seed=9, device=dev)
+    settings = [R.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, scene.bg.to(dev), 1.0,
+                                                c.world_view_transform, c.full_proj_transform, 2,
+                                                c.camera_center, False, False) for c in cams]
+    g = torch.Generator().manual_seed(3)
+    wc, wd, wa = (torch.randn(4, c, H, W, generator=g).to(dev) for c in (3, 1, 1))
+    res = []
+    for ms in (False, True, True):
+        R.set_multistream(ms)
+        d = scene.inputs(dev, requires_grad=True)
+        d["means2D"].retain_grad()
+        color, radii, depth, alpha = R.rasterize_views(settings, means3D=d["means3D"], means2D=d["means2D"],
+                                                       shs=d["shs"], opacities=d["opacities"], scales=d["scales"],
+                                                       rotations=d["rotations"])
+        ((color * wc).sum() + (depth * wd).sum() + (alpha * wa).sum()).backward()
+        torch.cuda.synchronize()
+        res.append((color, radii, depth, alpha, {k: d[k].grad.clone() for k in
+                                                 ("means3D", "means2D", "shs", "opacities", "scales", "rotations")}))
+    R.set_multistream(True)
+    for other in res[1:]:
+        for i in range(4):
+            assert torch.equal(res[0][i], other[i])
+        for k, gref in res[0][4].items():
+            _grad_close(k, other[4][k], gref, rtol=2e-5)
