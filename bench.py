@@ -273,7 +273,7 @@ def main():
     _lib.profile_enable(True)
     launches0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    d_sum = 0
+    st0 = rasterizer.stats()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -284,7 +284,6 @@ def main():
         ev[k][0].record()
         run_step(a.warmup + k, cams_all[a.warmup + k])
         ev[k][1].record()
-        d_sum += rasterizer._workspace(dev).last_num_rendered
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clock_info = clocks.stop() if rank == 0 else None
@@ -379,7 +378,8 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-    D = d_sum / max(1, a.steps)              # D of the last view of each step, averaged
+    st1 = rasterizer.stats()
+    D = (st1["num_rendered_sum"] - st0["num_rendered_sum"]) / max(1, st1["views"] - st0["views"])   # mean D per view
     HW, P, K = a.res * a.res, a.points, (a.sh_degree + 1) ** 2
     alg_bytes = {   # SURVEY.md §8(d) per-stage algorithmic bytes
         "preprocess_fwd": P * (44 + 12 * K + 48), "depth_sort": 4 * 16 * P, "scan_emit": 8 * P + 20 * P + 12 * D,

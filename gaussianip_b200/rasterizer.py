@@ -226,6 +226,9 @@ class _ForwardCall:
             with torch.cuda.stream(self.stream):
                 self.enqueue()
         ws.last_num_rendered = D
+        _stats["num_rendered"] = D
+        _stats["views"] += 1
+        _stats["num_rendered_sum"] += D
         # follow the scene downwards slowly so one huge view does not pin memory forever
         if D * 4 < ws.d_cap and ws.d_cap > max(1 << 16, 4 * P):
             ws.d_cap = max(1 << 16, 4 * P, 2 * D)
@@ -244,6 +247,12 @@ def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D,
 # streams and one view's sort overlaps another view's blend.
 _side_streams = {}
 _multistream = True
+_stats = {"num_rendered": 0, "views": 0, "num_rendered_sum": 0}
+
+
+def stats() -> dict:
+    """Host-side counters: D (num_rendered) of the last view, number of views, sum of D."""
+    return dict(_stats)
 
 
 def set_multistream(enabled: bool) -> None:
