@@ -313,7 +313,9 @@ scan_blocksums_kernel(uint32_t* __restrict__ blocksums, int num_blocks, uint32_t
     const unsigned long long D = carry;
     counts[CNT_D] = D > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)D;
     counts[CNT_OVERFLOW] = D > (unsigned long long)D_cap ? 1u : 0u;
+    counts[CNT_VISIBLE] = 0; counts[CNT_MAXTILES] = 0;   // reserved; the whole block is copied to the host
     counts[4] = (uint32_t)mode;
+    counts[5] = 0; counts[6] = 0; counts[7] = 0;
   }
 }
 
