@@ -245,9 +245,13 @@ def main():
     w_depth = torch.stack([w[1] for w in weights])
     w_alpha = torch.stack([w[2] for w in weights])
 
+    wc_flat, wd_flat, wa_flat = w_color.reshape(-1), w_depth.reshape(-1), w_alpha.reshape(-1)
+
     def loss_of(views, out):
-        return (out["render"] * w_color).sum() + (out["depth_3dgs"] * w_depth).sum() + \
-            (out["alpha_3dgs"] * w_alpha).sum()
+        # L = sum_views <w_c, colour> + <w_d, depth> + <w_a, alpha>  (SURVEY.md §8d): dense, non-trivial
+        # dL/dcolour, dL/ddepth, dL/dalpha; written as dot products (one reduction kernel each)
+        return torch.dot(out["render"].reshape(-1), wc_flat) + torch.dot(out["depth_3dgs"].reshape(-1), wd_flat) + \
+            torch.dot(out["alpha_3dgs"].reshape(-1), wa_flat)
 
     def run_step(step_idx, cams):
         # public API: all views of the step in one batched render call (same kernels per view as
