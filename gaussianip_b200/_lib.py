@@ -10,6 +10,7 @@ LIB_PATH = _PKG / "libgsb.so"
 
 GSB_OK, GSB_E_INVALID, GSB_E_CUDA, GSB_E_CAPACITY, GSB_E_UNSUPPORTED = 0, -1, -2, -3, -4
 BIN_TWO_LEVEL, BIN_FLAT64 = 0, 1
+MAX_VIEWS = 8
 
 
 class GsbSettings(C.Structure):
@@ -50,6 +51,7 @@ _PROTOS = {
     "gsb_read_counts": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_longlong, _P, _P]),
     "gsb_render_bwd": (C.c_int, [C.POINTER(GsbSettings), C.c_int, _P, _P, C.c_longlong, _P, _P, _P, _P]),
     "gsb_preprocess_bwd": (C.c_int, [C.POINTER(GsbSettings), C.c_int, C.c_int] + [_P] * 8 + [_P, _P, C.c_longlong] + [_P] * 8 + [C.c_int, _P]),
+    "gsb_preprocess_bwd_views": (C.c_int, [C.c_int, _P, C.c_int, C.c_int] + [_P] * 7 + [_P, _P, _P, _P] + [_P] * 8 + [C.c_int, _P]),
     "gsb_backward": (C.c_int, [C.POINTER(GsbSettings), C.c_int, C.c_int] + [_P] * 8 + [_P, _P, C.c_longlong] + [_P] * 3 + [_P] * 8 + [C.c_int, _P]),
     "gsb_profile_enable": (C.c_int, [C.c_int]),
     "gsb_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -238,6 +238,47 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
                            at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
 }
 
+int gsb_preprocess_bwd_views(int V, const GsbSettings* const* settings, int P, int K, const float* means3D,
+                             const float* scales, const float* rotations, const float* opacities,
+                             const float* shs, const float* colors_precomp, const float* cov3D_precomp,
+                             const int32_t* const* radii, const void* const* saved, const void* const* scratch,
+                             const long long* D_cap, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs,
+                             float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                             float* dL_dcov3D, int accumulate, void* stream) {
+  (void)opacities;
+  if (V < 1 || V > GSB_MAX_VIEWS || P < 0 || !settings || !radii || !saved || !scratch || !D_cap)
+    return GSB_E_INVALID;
+  if (P == 0) return GSB_OK;
+  if (!means3D || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacities) return GSB_E_INVALID;
+  if ((shs != nullptr) == (colors_precomp != nullptr)) return GSB_E_INVALID;
+  if ((cov3D_precomp != nullptr) == (scales != nullptr && rotations != nullptr)) return GSB_E_INVALID;
+  if (shs && !dL_dshs) return GSB_E_INVALID;
+  if (colors_precomp && !dL_dcolors) return GSB_E_INVALID;
+  if (cov3D_precomp && !dL_dcov3D) return GSB_E_INVALID;
+  if (!cov3D_precomp && (!dL_dscales || !dL_drotations)) return GSB_E_INVALID;
+  BwdBatch B;
+  B.V = V;
+  bool debug = false;
+  for (int v = 0; v < V; ++v) {
+    const GsbSettings* s = settings[v];
+    if (!settings_ok(s) || !radii[v] || !saved[v] || !scratch[v]) return GSB_E_INVALID;
+    if (shs && K < (s->sh_degree + 1) * (s->sh_degree + 1)) return GSB_E_INVALID;
+    GsbLayout L;
+    int rc = layout(P, s->image_height, s->image_width, D_cap[v], &L);
+    if (rc) return rc;
+    B.a[v].v = make_view(s);
+    B.a[v].geom = at<Geom>(saved[v], L.off_geom);
+    B.a[v].clamped = at<uint8_t>(saved[v], L.off_clamped);
+    B.a[v].ggrad = at<GGrad>(scratch[v], L.off_ggrad);
+    B.a[v].radii = radii[v];
+    debug = debug || s->debug != 0;
+  }
+  ProfScope ps(GSB_STAGE_PREPROCESS_BWD, (cudaStream_t)stream);
+  return launch_preprocess_bwd(B, P, K, means3D, scales, rotations, shs, colors_precomp, cov3D_precomp,
+                               dL_dmeans3D, dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacities, dL_dscales,
+                               dL_drotations, dL_dcov3D, accumulate, debug, (cudaStream_t)stream);
+}
+
 int gsb_preprocess_bwd(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
                        const float* rotations, const float* opacities, const float* shs,
                        const float* colors_precomp, const float* cov3D_precomp, const int32_t* radii,
@@ -245,26 +286,10 @@ int gsb_preprocess_bwd(const GsbSettings* s, int P, int K, const float* means3D,
                        float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors, float* dL_dopacities,
                        float* dL_dscales, float* dL_drotations, float* dL_dcov3D, int accumulate,
                        void* stream) {
-  if (!settings_ok(s) || P < 0) return GSB_E_INVALID;
-  if (P == 0) return GSB_OK;
-  if (!means3D || !radii || !saved || !scratch || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacities)
-    return GSB_E_INVALID;
-  if ((shs != nullptr) == (colors_precomp != nullptr)) return GSB_E_INVALID;
-  if ((cov3D_precomp != nullptr) == (scales != nullptr && rotations != nullptr)) return GSB_E_INVALID;
-  if (shs && !dL_dshs) return GSB_E_INVALID;
-  if (colors_precomp && !dL_dcolors) return GSB_E_INVALID;
-  if (cov3D_precomp && !dL_dcov3D) return GSB_E_INVALID;
-  if (!cov3D_precomp && (!dL_dscales || !dL_drotations)) return GSB_E_INVALID;
-  GsbLayout L;
-  int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
-  if (rc) return rc;
-  ProfScope ps(GSB_STAGE_PREPROCESS_BWD, (cudaStream_t)stream);
-  return launch_preprocess_bwd(make_view(s), P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
-                               cov3D_precomp, radii, at<Geom>(saved, L.off_geom),
-                               at<uint8_t>(saved, L.off_clamped), at<GGrad>(scratch, L.off_ggrad), dL_dmeans3D,
-                               dL_dmeans2D, shs ? dL_dshs : nullptr, colors_precomp ? dL_dcolors : nullptr,
-                               dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, accumulate, s->debug != 0,
-                               (cudaStream_t)stream);
+  return gsb_preprocess_bwd_views(1, &s, P, K, means3D, scales, rotations, opacities, shs, colors_precomp,
+                                  cov3D_precomp, &radii, &saved, &scratch, &D_cap, dL_dmeans3D, dL_dmeans2D,
+                                  dL_dshs, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D,
+                                  accumulate, stream);
 }
 
 int gsb_backward(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,

@@ -110,13 +110,22 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
                       const float* final_T, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                       GGrad* ggrad, bool debug, cudaStream_t st);
 
-int launch_preprocess_bwd(const View& v, int P, int K, const float* means3D, const float* scales,
-                          const float* rots, const float* opac, const float* shs,
-                          const float* colors, const float* cov3D, const int32_t* radii,
-                          const Geom* geom, const uint8_t* clamped, const GGrad* ggrad,
-                          float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors,
-                          float* dopac, float* dscales, float* drots, float* dcov3D,
-                          int accumulate, bool debug, cudaStream_t st);
+struct BwdView {          // one view of a (batched) preprocess backward
+  View v;
+  const Geom* geom;
+  const uint8_t* clamped;
+  const GGrad* ggrad;
+  const int32_t* radii;
+};
+struct BwdBatch {
+  int V;
+  BwdView a[GSB_MAX_VIEWS];
+};
+int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D, const float* scales,
+                          const float* rots, const float* shs, const float* colors, const float* cov3D,
+                          float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors, float* dopac,
+                          float* dscales, float* drots, float* dcov3D, int accumulate, bool debug,
+                          cudaStream_t st);
 
 // radix sort (binning.cu)
 size_t radix_tmp_bytes(long long n_cap);

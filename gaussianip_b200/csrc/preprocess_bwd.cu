@@ -5,7 +5,9 @@
 // colour.  One thread per Gaussian; the forward intermediates are recomputed from the
 // inputs instead of being stored (saves 24 B/Gaussian of cov3D traffic each way).
 // With accumulate != 0 results are added to the outputs (beta = 1) so all views of a step
-// land in one gradient bucket.
+// land in one gradient bucket.  The kernel takes up to GSB_MAX_VIEWS views at once: the
+// per-view contributions are summed in registers and every output is written ONCE, instead of
+// one read-modify-write of all gradient tensors per view.
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -14,37 +16,18 @@ namespace {
 
 __device__ __forceinline__ void put(float* p, float v, int acc) { *p = acc ? (*p + v) : v; }
 
-__global__ void __launch_bounds__(256)
-preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
-                      const float* __restrict__ scales, const float* __restrict__ rots,
-                      const float* __restrict__ shs, const float* __restrict__ cov3Dp,
-                      const int32_t* __restrict__ radii, const Geom* __restrict__ geom,
-                      const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, float* __restrict__ dmeans3D,
-                      float* __restrict__ dmeans2D, float* __restrict__ dshs, float* __restrict__ dcolors,
-                      float* __restrict__ dopac, float* __restrict__ dscales, float* __restrict__ drots,
-                      float* __restrict__ dcov3D, int acc) {
-  __shared__ float sV[16], sM[16], sCam[3];
-  if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sM[threadIdx.x] = v.proj[threadIdx.x]; }
-  if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
+struct Accum {            // per-Gaussian gradient sums over the views of one launch
+  float dp[3], d2[2], dop, dsc[3], dq[4], dcov[6], dcol[3];
+  float dsh[48];
+};
+
+// Adds the contribution of ONE view to the sums in A (Gaussian i is visible in that view).
+__device__ __forceinline__ void
+view_contrib(const View& v, int i, int K, const float* sV, const float* sM, const float* sCam,
+             const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rots,
+             const float* __restrict__ shs, const float* __restrict__ cov3Dp, const Geom* __restrict__ geom,
+             const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, bool precomp_color, Accum& A) {
   const int ncoef = (v.sh_degree + 1) * (v.sh_degree + 1);
-
-  if (radii[i] <= 0) {
-    if (!acc) {  // gradients of culled Gaussians are exactly 0
-      dmeans3D[3 * i] = dmeans3D[3 * i + 1] = dmeans3D[3 * i + 2] = 0.f;
-      dmeans2D[3 * i] = dmeans2D[3 * i + 1] = dmeans2D[3 * i + 2] = 0.f;
-      dopac[i] = 0.f;
-      if (dshs) for (int k = 0; k < 3 * K; ++k) dshs[(size_t)i * K * 3 + k] = 0.f;
-      if (dcolors) dcolors[3 * i] = dcolors[3 * i + 1] = dcolors[3 * i + 2] = 0.f;
-      if (dscales) dscales[3 * i] = dscales[3 * i + 1] = dscales[3 * i + 2] = 0.f;
-      if (drots) reinterpret_cast<float4*>(drots)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (dcov3D) for (int k = 0; k < 6; ++k) dcov3D[6 * (size_t)i + k] = 0.f;
-    }
-    return;
-  }
-
   const float4* gp = reinterpret_cast<const float4*>(ggrad + i);
   const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
   // moments -> gradients of the screen-space mean (NDC units) and of the conic
@@ -61,8 +44,8 @@ preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
   float dpx = 0.f, dpy = 0.f, dpz = 0.f;
 
   // ---- colour -------------------------------------------------------------------------
-  if (dcolors) {
-    put(dcolors + 3 * i, grgb[0], acc); put(dcolors + 3 * i + 1, grgb[1], acc); put(dcolors + 3 * i + 2, grgb[2], acc);
+  if (precomp_color) {
+    A.dcol[0] += grgb[0]; A.dcol[1] += grgb[1]; A.dcol[2] += grgb[2];
   } else {
     const uint8_t cl = clamped[i];
     if (cl & 1) grgb[0] = 0.f;
@@ -73,7 +56,6 @@ preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
     const float inv = rsqrtf(sum2);
     const float x = ox * inv, y = oy * inv, z = oz * inv;
     const float* sh = shs + (size_t)i * K * 3;
-    float* dsh = dshs + (size_t)i * K * 3;
     const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
     float basis[16];
     float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
@@ -121,13 +103,9 @@ preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
         }
       }
     }
-    for (int k = 0; k < K; ++k) {
-      const float bk = k < ncoef ? basis[k] : 0.f;
+    for (int k = 0; k < ncoef; ++k) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (k < ncoef) put(dsh + 3 * k + c, bk * grgb[c], acc);
-        else if (!acc) dsh[3 * k + c] = 0.f;
-      }
+      for (int c = 0; c < 3; ++c) A.dsh[3 * k + c] += basis[k] * grgb[c];
     }
     // through the view direction normalisation
     const float dLx = ddx[0] * grgb[0] + ddx[1] * grgb[1] + ddx[2] * grgb[2];
@@ -233,16 +211,14 @@ preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
   dpy += (sM[4] * pw - sM[7] * mul1) * gx + (sM[5] * pw - sM[7] * mul2) * gy + sV[6] * gdepth;
   dpz += (sM[8] * pw - sM[11] * mul1) * gx + (sM[9] * pw - sM[11] * mul2) * gy + sV[10] * gdepth;
 
-  put(dmeans3D + 3 * i, dpx, acc); put(dmeans3D + 3 * i + 1, dpy, acc); put(dmeans3D + 3 * i + 2, dpz, acc);
-  put(dmeans2D + 3 * i, gx, acc); put(dmeans2D + 3 * i + 1, gy, acc);
-  if (!acc) dmeans2D[3 * i + 2] = 0.f;
-  put(dopac + i, gop, acc);
+  A.dp[0] += dpx; A.dp[1] += dpy; A.dp[2] += dpz;
+  A.d2[0] += gx; A.d2[1] += gy;
+  A.dop += gop;
 
   // ---- cov3D -> scale / rotation ---------------------------------------------------------
   if (cov3Dp) {
-    float* o = dcov3D + 6 * (size_t)i;
-    put(o + 0, Gs[0][0], acc); put(o + 1, 2.f * Gs[0][1], acc); put(o + 2, 2.f * Gs[0][2], acc);
-    put(o + 3, Gs[1][1], acc); put(o + 4, 2.f * Gs[1][2], acc); put(o + 5, Gs[2][2], acc);
+    A.dcov[0] += Gs[0][0]; A.dcov[1] += 2.f * Gs[0][1]; A.dcov[2] += 2.f * Gs[0][2];
+    A.dcov[3] += Gs[1][1]; A.dcov[4] += 2.f * Gs[1][2]; A.dcov[5] += Gs[2][2];
   } else {
     float dM[3][3];
 #pragma unroll
@@ -252,43 +228,100 @@ preprocess_bwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
         dM[p][k] = 2.f * (Gs[p][0] * m[0][k] + Gs[p][1] * m[1][k] + Gs[p][2] * m[2][k]);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      put(dscales + 3 * i + k, v.scale_mod * (R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k]), acc);
+      A.dsc[k] += v.scale_mod * (R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k]);
     float dR[3][3];
 #pragma unroll
     for (int p = 0; p < 3; ++p)
 #pragma unroll
       for (int k = 0; k < 3; ++k) dR[p][k] = s[k] * dM[p][k];
-    const float dqr = 2.f * (-qz * dR[0][1] + qy * dR[0][2] + qz * dR[1][0] - qx * dR[1][2] - qy * dR[2][0] + qx * dR[2][1]);
-    const float dqx = 2.f * (qy * dR[0][1] + qz * dR[0][2] + qy * dR[1][0] - 2.f * qx * dR[1][1] - qr * dR[1][2] +
-                             qz * dR[2][0] + qr * dR[2][1] - 2.f * qx * dR[2][2]);
-    const float dqy = 2.f * (-2.f * qy * dR[0][0] + qx * dR[0][1] + qr * dR[0][2] + qx * dR[1][0] + qz * dR[1][2] -
-                             qr * dR[2][0] + qz * dR[2][1] - 2.f * qy * dR[2][2]);
-    const float dqz = 2.f * (-2.f * qz * dR[0][0] - qr * dR[0][1] + qx * dR[0][2] + qr * dR[1][0] - 2.f * qz * dR[1][1] +
-                             qy * dR[1][2] + qx * dR[2][0] + qy * dR[2][1]);
+    A.dq[0] += 2.f * (-qz * dR[0][1] + qy * dR[0][2] + qz * dR[1][0] - qx * dR[1][2] - qy * dR[2][0] + qx * dR[2][1]);
+    A.dq[1] += 2.f * (qy * dR[0][1] + qz * dR[0][2] + qy * dR[1][0] - 2.f * qx * dR[1][1] - qr * dR[1][2] +
+                      qz * dR[2][0] + qr * dR[2][1] - 2.f * qx * dR[2][2]);
+    A.dq[2] += 2.f * (-2.f * qy * dR[0][0] + qx * dR[0][1] + qr * dR[0][2] + qx * dR[1][0] + qz * dR[1][2] -
+                      qr * dR[2][0] + qz * dR[2][1] - 2.f * qy * dR[2][2]);
+    A.dq[3] += 2.f * (-2.f * qz * dR[0][0] - qr * dR[0][1] + qx * dR[0][2] + qr * dR[1][0] - 2.f * qz * dR[1][1] +
+                      qy * dR[1][2] + qx * dR[2][0] + qy * dR[2][1]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3D,
+                      const float* __restrict__ scales, const float* __restrict__ rots,
+                      const float* __restrict__ shs, const float* __restrict__ cov3Dp,
+                      float* __restrict__ dmeans3D, float* __restrict__ dmeans2D, float* __restrict__ dshs,
+                      float* __restrict__ dcolors, float* __restrict__ dopac, float* __restrict__ dscales,
+                      float* __restrict__ drots, float* __restrict__ dcov3D, int acc) {
+  __shared__ float sV[GSB_MAX_VIEWS][16], sM[GSB_MAX_VIEWS][16], sCam[GSB_MAX_VIEWS][4];
+  for (int t = threadIdx.x; t < B.V * 16; t += blockDim.x) {
+    sV[t >> 4][t & 15] = B.a[t >> 4].v.view[t & 15];
+    sM[t >> 4][t & 15] = B.a[t >> 4].v.proj[t & 15];
+  }
+  for (int t = threadIdx.x; t < B.V * 3; t += blockDim.x) sCam[t / 3][t % 3] = B.a[t / 3].v.campos[t % 3];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+
+  Accum A;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { A.dp[k] = 0.f; A.dsc[k] = 0.f; A.dcol[k] = 0.f; }
+  A.d2[0] = A.d2[1] = 0.f; A.dop = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) A.dq[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) A.dcov[k] = 0.f;
+  const int ncoef_max = dshs ? min(K, 16) : 0;
+  for (int k = 0; k < 3 * ncoef_max; ++k) A.dsh[k] = 0.f;
+
+  for (int vi = 0; vi < B.V; ++vi) {
+    const BwdView& bv = B.a[vi];
+    if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
+    view_contrib(bv.v, i, K, sV[vi], sM[vi], sCam[vi], means3D, scales, rots, shs, cov3Dp, bv.geom, bv.clamped,
+                 bv.ggrad, dcolors != nullptr, A);
+  }
+
+  put(dmeans3D + 3 * i, A.dp[0], acc); put(dmeans3D + 3 * i + 1, A.dp[1], acc); put(dmeans3D + 3 * i + 2, A.dp[2], acc);
+  put(dmeans2D + 3 * i, A.d2[0], acc); put(dmeans2D + 3 * i + 1, A.d2[1], acc);
+  if (!acc) dmeans2D[3 * i + 2] = 0.f;
+  put(dopac + i, A.dop, acc);
+  if (dcolors) {
+    put(dcolors + 3 * i, A.dcol[0], acc); put(dcolors + 3 * i + 1, A.dcol[1], acc); put(dcolors + 3 * i + 2, A.dcol[2], acc);
+  }
+  if (dshs) {
+    float* dsh = dshs + (size_t)i * K * 3;
+    for (int k = 0; k < 3 * K; ++k) {
+      if (k < 3 * ncoef_max) put(dsh + k, A.dsh[k], acc);
+      else if (!acc) dsh[k] = 0.f;
+    }
+  }
+  if (cov3Dp) {
+    float* o = dcov3D + 6 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) put(o + k, A.dcov[k], acc);
+  } else {
+    put(dscales + 3 * i, A.dsc[0], acc); put(dscales + 3 * i + 1, A.dsc[1], acc); put(dscales + 3 * i + 2, A.dsc[2], acc);
     float4* o = reinterpret_cast<float4*>(drots) + i;
     if (acc) {
       const float4 old = *o;
-      *o = make_float4(old.x + dqr, old.y + dqx, old.z + dqy, old.w + dqz);
+      *o = make_float4(old.x + A.dq[0], old.y + A.dq[1], old.z + A.dq[2], old.w + A.dq[3]);
     } else {
-      *o = make_float4(dqr, dqx, dqy, dqz);
+      *o = make_float4(A.dq[0], A.dq[1], A.dq[2], A.dq[3]);
     }
   }
 }
 
 }  // namespace
 
-int launch_preprocess_bwd(const View& v, int P, int K, const float* means3D, const float* scales,
-                          const float* rots, const float* opac, const float* shs,
-                          const float* colors, const float* cov3D, const int32_t* radii,
-                          const Geom* geom, const uint8_t* clamped, const GGrad* ggrad,
-                          float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors,
-                          float* dopac, float* dscales, float* drots, float* dcov3D,
-                          int accumulate, bool debug, cudaStream_t st) {
-  (void)opac; (void)colors;
+int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D, const float* scales,
+                          const float* rots, const float* shs, const float* colors, const float* cov3D,
+                          float* dmeans3D, float* dmeans2D, float* dshs, float* dcolors, float* dopac,
+                          float* dscales, float* drots, float* dcov3D, int accumulate, bool debug,
+                          cudaStream_t st) {
   if (P == 0) return GSB_OK;
-  preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(v, P, K, means3D, scales, rots, shs, cov3D, radii,
-                                                         geom, clamped, ggrad, dmeans3D, dmeans2D, dshs, dcolors,
-                                                         dopac, dscales, drots, dcov3D, accumulate);
+  if (B.V < 1 || B.V > GSB_MAX_VIEWS) return GSB_E_INVALID;
+  preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(B, P, K, means3D, scales, rots, shs, cov3D, dmeans3D,
+                                                         dmeans2D, shs ? dshs : nullptr,
+                                                         colors ? dcolors : nullptr, dopac, dscales, drots, dcov3D,
+                                                         accumulate);
   GSB_POST_LAUNCH(debug, st, "preprocess_bwd_kernel");
   return GSB_OK;
 }

@@ -349,17 +349,25 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
                 done = torch.cuda.Event()
                 done.record(st)
             staged.append((s, keep, scratch, done))
-        for v, (rs, sv) in enumerate(zip(settings_list, svs)):
-            s, keep, scratch, done = staged[v]
-            main.wait_event(done)
+        # one fused per-Gaussian kernel over all views: contributions summed in registers, every
+        # gradient tensor written once (instead of V read-modify-write passes)
+        for v, sv in enumerate(svs):
+            main.wait_event(staged[v][3])
             sv.block.record_stream(main)
-            rc = lib.gsb_preprocess_bwd(C.byref(s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
-                                        _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), radii[v].data_ptr(),
-                                        sv.block.data_ptr(), scratch.data_ptr(), sv.d_cap, _ptr(out["means3D"]),
-                                        _ptr(out["means2D"]), _ptr(out["shs"]), _ptr(out["colors"]),
-                                        _ptr(out["opacities"]), _ptr(out["scales"]), _ptr(out["rotations"]),
-                                        _ptr(out["cov3D"]), int(v > 0), main.cuda_stream)
-            _lib.check(rc, "gsb_preprocess_bwd")
+        for v0 in range(0, V, _lib.MAX_VIEWS):
+            n = min(_lib.MAX_VIEWS, V - v0)
+            sp = (C.POINTER(_lib.GsbSettings) * n)(*[C.pointer(staged[v0 + j][0]) for j in range(n)])
+            rp = (C.c_void_p * n)(*[radii[v0 + j].data_ptr() for j in range(n)])
+            svp = (C.c_void_p * n)(*[svs[v0 + j].block.data_ptr() for j in range(n)])
+            scp = (C.c_void_p * n)(*[staged[v0 + j][2].data_ptr() for j in range(n)])
+            dcp = (C.c_longlong * n)(*[svs[v0 + j].d_cap for j in range(n)])
+            rc = lib.gsb_preprocess_bwd_views(n, sp, P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
+                                              _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), rp, svp, scp,
+                                              dcp, _ptr(out["means3D"]), _ptr(out["means2D"]), _ptr(out["shs"]),
+                                              _ptr(out["colors"]), _ptr(out["opacities"]), _ptr(out["scales"]),
+                                              _ptr(out["rotations"]), _ptr(out["cov3D"]), int(v0 > 0),
+                                              main.cuda_stream)
+            _lib.check(rc, "gsb_preprocess_bwd_views")
         # the side streams' scratch blocks are read by the calling stream above; they are persistent
         # per-(device, stream) workspaces, so no allocator hand-over is involved
         for st in streams[:V]:

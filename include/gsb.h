@@ -146,6 +146,20 @@ int gsb_preprocess_bwd(const GsbSettings* s, int P, int K,
                        float* dL_dcolors, float* dL_dopacities, float* dL_dscales,
                        float* dL_drotations, float* dL_dcov3D, int accumulate, void* stream);
 
+/* Batched form of gsb_preprocess_bwd over V <= GSB_MAX_VIEWS views of the SAME Gaussians (the
+ * views of one optimisation step): the per-view contributions are summed in registers and each
+ * gradient tensor is written once.  settings[v], radii[v], saved[v], scratch[v], D_cap[v] describe
+ * view v exactly as in gsb_preprocess_bwd (all views share P, K, resolution may differ). */
+#define GSB_MAX_VIEWS 8
+int gsb_preprocess_bwd_views(int V, const GsbSettings* const* settings, int P, int K,
+                             const float* means3D, const float* scales, const float* rotations,
+                             const float* opacities, const float* shs, const float* colors_precomp,
+                             const float* cov3D_precomp, const int32_t* const* radii,
+                             const void* const* saved, const void* const* scratch, const long long* D_cap,
+                             float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs,
+                             float* dL_dcolors, float* dL_dopacities, float* dL_dscales,
+                             float* dL_drotations, float* dL_dcov3D, int accumulate, void* stream);
+
 /* Both backward stages — replaces `_C.rasterize_gaussians_backward`. */
 int gsb_backward(const GsbSettings* s, int P, int K,
                  const float* means3D, const float* scales, const float* rotations,
