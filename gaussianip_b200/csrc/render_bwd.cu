@@ -104,8 +104,7 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
               gC2 = inside ? dL_dcolor[2 * hw + pix] : 0.f;
   const float gD = inside ? dL_ddepth[pix] : 0.f, gA = inside ? dL_dalpha[pix] : 0.f;
   const float bg_dot = v.bg[0] * gC0 + v.bg[1] * gC1 + v.bg[2] * gC2;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
-  float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lD = 0.f;
+  float Bdot = T_final * bg_dot;     // see the derivation at its use
 
   float4 (*ring)[3][32] = s_rec[warp];
   uint32_t (*gring)[32] = s_gid[warp];
@@ -189,20 +188,16 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 #pragma unroll
         for (int j = 0; j < 12; ++j) g[i][j] = 0.0f;
         if (valid[i]) {
+          // With phi_j = <c_j, dL/dC> + depth_j dL/dD + dL/dA and the suffix sum
+          //   Bdot_i = T_final <bg, dL/dC> + sum_{j behind i} phi_j alpha_j T_j,
+          // dL/dalpha_i = T_i phi_i - Bdot_i / (1 - alpha_i): the reference's five "colour behind"
+          // recurrences collapse into ONE scalar (identical in exact arithmetic).
           const float inv1ma = __fdividef(1.0f, 1.0f - alpha[i]);
           T *= inv1ma;
           const float w = alpha[i] * T;
-          acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0; lc0 = f[i].y;
-          acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1; lc1 = f[i].z;
-          acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2; lc2 = f[i].w;
-          accD = last_alpha * lD + (1.0f - last_alpha) * accD; lD = f[i].x;
-          accA = last_alpha + (1.0f - last_alpha) * accA;
-          float dL_da = (f[i].y - acc0) * gC0 + (f[i].z - acc1) * gC1 + (f[i].w - acc2) * gC2;
-          dL_da += (f[i].x - accD) * gD;
-          dL_da += (1.0f - accA) * gA;
-          dL_da *= T;
-          last_alpha = alpha[i];
-          dL_da -= T_final * inv1ma * bg_dot;
+          const float phi = f[i].y * gC0 + f[i].z * gC1 + f[i].w * gC2 + f[i].x * gD + gA;
+          const float dL_da = T * phi - Bdot * inv1ma;
+          Bdot += phi * w;
           // raw moments of s = dL/dG * G about the splat centre; the linear maps to
           // d(ndc xy) and d(conic) are applied once per Gaussian in preprocess_bwd
           const float s_ = q[i].w * dL_da * G[i];
