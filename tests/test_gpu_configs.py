@@ -117,3 +117,30 @@ def test_config4_playback_forward_only(cuda_device):
             if prev is not None:
                 assert float((img - prev).abs().mean()) > 1e-4          # the avatar moves between frames
             prev = img
+
+
+@pytest.mark.timeout(600)
+def test_bench_size_view_against_oracle(cuda_device):
+    """The bench workload at FULL size — 1 M Gaussians, one 1024^2 AHDS view, colour+depth+alpha
+    fwd+bwd — against the CPU oracle on the same inputs (about 15-30 s of host time): bit-exact
+    radii / 2.0 M sorted keys / instance order / ranges, images within 1e-5, contributor counts
+    exact outside oracle-flagged marginal pixels, every gradient within 1e-4 of its max."""
+    from tests.test_gpu_parity import _gpu_forward_state, _grad_close
+    scene = util.humanoid_scene(P=1_000_000, H=1024, W=1024, sh_degree=0)
+    w = util.loss_weights(1024, 1024)
+    ref = util.run_oracle(scene, grads=w, requires_grad=True)
+    color, radii, depth, alpha, sv, keys = _gpu_forward_state(scene, cuda_device, "two_level")
+    g, b, img = ref["geom"], ref["binning"], ref["image"]
+    assert len(b.keys) > 1_500_000
+    assert torch.equal(radii.cpu(), g.radii)
+    assert np.array_equal(keys, b.keys)
+    assert np.array_equal(sv.point_list().cpu().numpy().astype(np.int64), b.point_list)
+    assert np.array_equal(sv.ranges().cpu().numpy().astype(np.int64), b.ranges)
+    for k, t in (("color", color), ("depth", depth), ("alpha", alpha)):
+        assert (t.cpu() - ref[k].detach()).abs().max().item() <= 1e-5, k
+    mism = (sv.n_contrib().cpu() != img.n_contrib) & ~img.marginal
+    assert int(mism.sum()) == 0 and float(img.marginal.float().mean()) < 0.02
+    got = util.run_gpu(scene, cuda_device, grads=w, requires_grad=True)
+    for k, rg in ref["grads"].items():
+        if rg is not None:
+            _grad_close(k, got["grads"][k], rg)
