@@ -49,13 +49,12 @@ __device__ __forceinline__ float sh_channel(int deg, const float* __restrict__ s
 
 __device__ __forceinline__ void
 preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, const float* sCam,
-               const float* mean3 /*this Gaussian's xyz*/, const float* scale3 /*its scales or null*/,
-               const float* __restrict__ rots, const float* __restrict__ opac, const float* sh_row /*[K,3] or null*/,
-               const float* color3 /*precomputed rgb or null*/, const float* __restrict__ cov3Dp,
-               int32_t* __restrict__ radii, Geom* __restrict__ geom, uint8_t* __restrict__ clamped,
-               ushort4* __restrict__ rect, uint32_t* __restrict__ tiles, uint32_t* __restrict__ dkeys,
-               uint32_t* s_h0) {
-  const float px = mean3[0], py = mean3[1], pz = mean3[2];
+               const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rots,
+               const float* __restrict__ opac, const float* __restrict__ shs, const float* __restrict__ colors,
+               const float* __restrict__ cov3Dp, int32_t* __restrict__ radii, Geom* __restrict__ geom,
+               uint8_t* __restrict__ clamped, ushort4* __restrict__ rect, uint32_t* __restrict__ tiles,
+               uint32_t* __restrict__ dkeys, uint32_t* s_h0) {
+  const float px = means3D[3 * i], py = means3D[3 * i + 1], pz = means3D[3 * i + 2];
   const float tx = ((sV[0] * px + sV[4] * py) + sV[8] * pz) + sV[12];
   const float ty = ((sV[1] * px + sV[5] * py) + sV[9] * pz) + sV[13];
   const float tz = ((sV[2] * px + sV[6] * py) + sV[10] * pz) + sV[14];
@@ -75,7 +74,8 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
       const float* c = cov3Dp + 6 * (size_t)i;
       S00 = c[0]; S01 = c[1]; S02 = c[2]; S11 = c[3]; S12 = c[4]; S22 = c[5];
     } else {
-      const float sx = v.scale_mod * scale3[0], sy = v.scale_mod * scale3[1], sz = v.scale_mod * scale3[2];
+      const float sx = v.scale_mod * scales[3 * i], sy = v.scale_mod * scales[3 * i + 1],
+                  sz = v.scale_mod * scales[3 * i + 2];
       const float4 q = reinterpret_cast<const float4*>(rots)[i];
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       const float m00 = (1.0f - 2.0f * (y * y + z * z)) * sx, m01 = (2.0f * (x * y - r * z)) * sy,
@@ -135,13 +135,13 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
         rad = (radf < 1073741824.0f) ? (int)radf : 1073741824;
         float r_, g_, b_;
         uint8_t cl = 0;
-        if (color3) {
-          r_ = color3[0]; g_ = color3[1]; b_ = color3[2];
+        if (colors) {
+          r_ = colors[3 * i]; g_ = colors[3 * i + 1]; b_ = colors[3 * i + 2];
         } else {
           const float dx = px - sCam[0], dy = py - sCam[1], dz = pz - sCam[2];
           const float ln = sqrtf((dx * dx + dy * dy) + dz * dz);
           const float x = dx / ln, y = dy / ln, z = dz / ln;
-          const float* sh = sh_row;
+          const float* sh = shs + (size_t)i * K * 3;
           r_ = sh_channel(v.sh_degree, sh, 0, x, y, z) + 0.5f;
           g_ = sh_channel(v.sh_degree, sh, 1, x, y, z) + 0.5f;
           b_ = sh_channel(v.sh_degree, sh, 2, x, y, z) + 0.5f;
@@ -194,41 +194,17 @@ preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
                       uint32_t* __restrict__ ghist0) {
   __shared__ float sV[16], sM[16], sCam[3];
   __shared__ uint32_t s_h0[256];   // digit-0 histogram of the depth keys (first pass of the depth sort)
-  // The [P,3] inputs (xyz, scales, degree-0 SH / precomputed colours) are rows of 12 B: a thread
-  // reading its own row is a stride-3 access.  The CTA's 1024 rows are instead staged with
-  // coalesced 16 B loads, all in flight at once, and read back conflict-free (stride 3 words).
-  constexpr int ROWS = 256 * PRE_IPT;
-  __shared__ __align__(16) float s_mean[3 * ROWS], s_scale[3 * ROWS], s_col[3 * ROWS];
   s_h0[threadIdx.x] = 0;
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sM[threadIdx.x] = v.proj[threadIdx.x]; }
   if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
-  const int base = blockIdx.x * ROWS;
-  const int rows = min(ROWS, P - base);
-  const float* col_src = colors ? colors : ((shs && K == 1) ? shs : nullptr);   // 3 floats per Gaussian
-  auto stage = [&](const float* src, float* dst) {
-    const float* g = src + 3 * (size_t)base;
-    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-      const int n4 = (3 * rows) >> 2;
-      for (int t = threadIdx.x; t < n4; t += 256) reinterpret_cast<float4*>(dst)[t] = reinterpret_cast<const float4*>(g)[t];
-      for (int t = (n4 << 2) + threadIdx.x; t < 3 * rows; t += 256) dst[t] = g[t];
-    } else {
-      for (int t = threadIdx.x; t < 3 * rows; t += 256) dst[t] = g[t];
-    }
-  };
-  stage(means3D, s_mean);
-  if (scales) stage(scales, s_scale);
-  if (col_src) stage(col_src, s_col);
   __syncthreads();
   // PRE_IPT Gaussians per thread: 4x fewer CTAs flushing their 256-bin histogram to the same
   // 256 global counters (one flush per 256 Gaussians cost +22 us of same-address L2 atomics)
 #pragma unroll 1
   for (int k = 0; k < PRE_IPT; ++k) {
-    const int r = k * 256 + threadIdx.x;
-    const int i = base + r;
-    if (i < P)
-      preprocess_one(v, i, K, sV, sM, sCam, s_mean + 3 * r, scales ? s_scale + 3 * r : nullptr, rots, opac,
-                     shs ? (K == 1 ? s_col + 3 * r : shs + (size_t)i * K * 3) : nullptr,
-                     colors ? s_col + 3 * r : nullptr, cov3Dp, radii, geom, clamped, rect, tiles, dkeys, s_h0);
+    const int i = (blockIdx.x * PRE_IPT + k) * 256 + threadIdx.x;
+    if (i < P) preprocess_one(v, i, K, sV, sM, sCam, means3D, scales, rots, opac, shs, colors, cov3Dp, radii, geom,
+                              clamped, rect, tiles, dkeys, s_h0);
   }
   __syncthreads();
   if (s_h0[threadIdx.x]) atomicAdd(&ghist0[threadIdx.x], s_h0[threadIdx.x]);

@@ -21,6 +21,10 @@ constexpr int WARPS = 8;
 #define GSB_BWD_STAGES 2
 #endif
 constexpr int STAGES = GSB_BWD_STAGES;
+#ifndef GSB_BWD_HB
+#define GSB_BWD_HB 1
+#endif
+constexpr int BH = GSB_BWD_HB;       // hits evaluated together
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -156,20 +160,20 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       hit = (fabsf(a.x - cxw) <= a.z + hwx) && (fabsf(a.y - cyw) <= a.w + hwy);
     }
     uint32_t mask = __ballot_sync(0xffffffffu, hit);
-    // Hits are taken two at a time (back to front): the geometry/alpha of both are independent
-    // and the two 13-shuffle reductions interleave, hiding most of their latency chains.
+    // Hits are taken BH at a time (back to front): their geometry/alpha are independent and the
+    // 13-shuffle reductions can interleave.
     while (mask) {
-      int k[2];
+      int k[BH];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < BH; ++i) {
         k[i] = mask ? 31 - __clz(mask) : -1;
         if (k[i] >= 0) mask &= ~(1u << k[i]);
       }
-      float dx[2], dy[2], G[2], alpha[2];
-      float4 q[2], f[2];
-      bool valid[2];
+      float dx[BH], dy[BH], G[BH], alpha[BH];
+      float4 q[BH], f[BH];
+      bool valid[BH];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < BH; ++i) {
         valid[i] = false;
         if (k[i] >= 0) {
           const float4 a = st[0][k[i]];
@@ -182,9 +186,9 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           valid[i] = ((uint32_t)(base + k[i] + 1) <= my_last) && power <= 0.0f && alpha[i] >= ALPHA_MIN;
         }
       }
-      float g[2][12];
+      float g[BH][12];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < BH; ++i) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) g[i][j] = 0.0f;
         if (valid[i]) {
@@ -213,26 +217,16 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           g[i][9] = w * gC2;
         }
       }
-      const bool any0 = __any_sync(0xffffffffu, valid[0]);
-      const bool any1 = __any_sync(0xffffffffu, valid[1]);
       const int slot = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
       const bool writer = !(lane & 1) && !((lane & 4) && (lane & 2)) && slot < 10;
-      float tot0 = 0.0f, tot1 = 0.0f;
-      if (any0 && any1) {
-        tot0 = butterfly12(g[0], lane);
-        tot1 = butterfly12(g[1], lane);
-      } else if (any0) {
-        tot0 = butterfly12(g[0], lane);
-      } else if (any1) {
-        tot1 = butterfly12(g[1], lane);
-      }
       // (direct per-lane atomics for splats that only graze the warp were measured slower:
       //  521 -> 560 us at FRINGE=3, 569 us at FRINGE=1; the butterfly is kept for every hit)
-      if (writer) {
-        if (any0 && tot0 != 0.0f)
-          atomicAdd(reinterpret_cast<float*>(ggrad + gring[c & (STAGES - 1)][k[0]]) + slot, tot0);
-        if (any1 && tot1 != 0.0f)
-          atomicAdd(reinterpret_cast<float*>(ggrad + gring[c & (STAGES - 1)][k[1]]) + slot, tot1);
+#pragma unroll
+      for (int i = 0; i < BH; ++i) {
+        if (!__any_sync(0xffffffffu, valid[i])) continue;
+        const float tot = butterfly12(g[i], lane);
+        if (writer && tot != 0.0f)
+          atomicAdd(reinterpret_cast<float*>(ggrad + gring[c & (STAGES - 1)][k[i]]) + slot, tot);
       }
     }
     __syncwarp();

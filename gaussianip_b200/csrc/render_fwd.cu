@@ -21,7 +21,10 @@ namespace gsb {
 namespace {
 
 constexpr int WARPS = 8;
-constexpr int HB = 4;          // hits evaluated together (ILP)
+#ifndef GSB_FWD_HB
+#define GSB_FWD_HB 2
+#endif
+constexpr int HB = GSB_FWD_HB;   // hits evaluated together (ILP)
 #ifndef GSB_FWD_STAGES
 #define GSB_FWD_STAGES 2
 #endif
