@@ -243,7 +243,11 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
   GSB_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)P * sizeof(GGrad), st));
   const int T = v.gx * v.gy;
   if (T == 0 || P == 0) return GSB_OK;
-  constexpr size_t smem = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
+#ifndef GSB_BWD_SMEM_PAD
+#define GSB_BWD_SMEM_PAD 0
+#endif
+  // (padding = an occupancy cap for tuning sweeps: shared memory not used by CTAs stays L1)
+  constexpr size_t smem = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t)) + GSB_BWD_SMEM_PAD;
   static bool configured[64] = {};   // the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));

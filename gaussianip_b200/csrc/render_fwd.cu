@@ -181,7 +181,10 @@ int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_lis
                       uint32_t* n_contrib, float* final_T, bool debug, cudaStream_t st) {
   const int T = v.gx * v.gy;
   if (T == 0) return GSB_OK;
-  constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4);
+#ifndef GSB_FWD_SMEM_PAD
+#define GSB_FWD_SMEM_PAD 0
+#endif
+  constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4) + GSB_FWD_SMEM_PAD;
   static bool configured[64] = {};   // the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
