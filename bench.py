@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--views", type=int, default=4, help="views per step per GPU")
     ap.add_argument("--sh-degree", type=int, default=0)
+    ap.add_argument("--variant", default="native", choices=["native", "standin"],
+                    help="standin = reference-STRUCTURE kernels of csrc/standin.cu + 64-bit key sort + per-view "
+                         "Python loop, for context only (never the reference, never the product)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -240,6 +243,10 @@ def main():
 
     vp = multiview.ViewParallel(params, a.points)
     model = Model(params)
+    standin = a.variant == "standin"
+    if standin:
+        rasterizer.set_blend_variant("standin")
+        rasterizer.set_binning_mode("flat64", dev)
 
     w_color = torch.stack([w[0] for w in weights])
     w_depth = torch.stack([w[1] for w in weights])
@@ -253,7 +260,15 @@ def main():
         return torch.dot(out["render"].reshape(-1), wc_flat) + torch.dot(out["depth_3dgs"].reshape(-1), wd_flat) + \
             torch.dot(out["alpha_3dgs"].reshape(-1), wa_flat)
 
+    def loss_one(v, out):
+        return torch.dot(out["render"].reshape(-1), w_color[v].reshape(-1)) + \
+            torch.dot(out["depth_3dgs"].reshape(-1), w_depth[v].reshape(-1)) + \
+            torch.dot(out["alpha_3dgs"].reshape(-1), w_alpha[v].reshape(-1))
+
     def run_step(step_idx, cams):
+        if standin:     # the reference's structure: one render() call per view from a Python loop
+            return vp.step(a.views, lambda v, vsp: renderer.render(cams[v], model, None, bg, screenspace_points=vsp),
+                           loss_one, views=range(a.views))
         # public API: all views of the step in one batched render call (same kernels per view as
         # the single-view operator; activations evaluated once per step, one autograd node)
         def render_views_fn(views, vsp):
@@ -417,7 +432,9 @@ def main():
         vps, cores, sample, _ = cpu_reference_run(a, 1, 0, 40.0)
         cpu = {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    line = {"variant": "reference-STRUCTURE stand-in (csrc/standin.cu + flat 64-bit sort + per-view loop); NOT the "
+                       "reference and NOT the product path"} if standin else {}
+    line.update({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "points": a.points, "resolution": a.res,
@@ -428,7 +445,7 @@ def main():
                        "wall_s_timed_region": t_wall},
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu})
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

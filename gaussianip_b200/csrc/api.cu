@@ -19,6 +19,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_blend_variant{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- stage profiler ------------------------------------------------------------------------
@@ -151,6 +152,12 @@ int gsb_profile_read(float* ms_out, int* calls_out) {
 
 long long gsb_launch_count(void) { return g_launches.load(); }
 
+int gsb_set_blend_variant(int variant) {
+  if (variant != 0 && variant != 1) return GSB_E_INVALID;
+  g_blend_variant.store(variant);
+  return GSB_OK;
+}
+
 int gsb_layout(int P, int H, int W, long long D_cap, GsbLayout* out) { return layout(P, H, W, D_cap, out); }
 
 int gsb_preprocess_fwd(const GsbSettings* s, int P, int K, const float* means3D, const float* scales,
@@ -193,6 +200,11 @@ int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap, fl
   int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
   if (rc) return rc;
   ProfScope ps(GSB_STAGE_RENDER_FWD, (cudaStream_t)stream);
+  if (g_blend_variant.load() == 1)
+    return launch_standin_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
+                              at<uint2>(saved, L.off_ranges), out_color, out_depth, out_alpha,
+                              at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
+                              (cudaStream_t)stream);
   return launch_render_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order), out_color,
                            out_depth, out_alpha,
@@ -232,6 +244,11 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
   int rc = layout(P, s->image_height, s->image_width, D_cap, &L);
   if (rc) return rc;
   ProfScope ps(GSB_STAGE_RENDER_BWD, (cudaStream_t)stream);
+  if (g_blend_variant.load() == 1)
+    return launch_standin_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
+                              at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_n_contrib),
+                              at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
+                              at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
   return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order),
                            at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,

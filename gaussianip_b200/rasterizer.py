@@ -255,6 +255,12 @@ def stats() -> dict:
     return dict(_stats)
 
 
+def set_blend_variant(name: str) -> None:
+    """'native' (default, the product kernels) or 'standin' (reference-STRUCTURE blend kernels of
+    csrc/standin.cu, for measurement context and GPU cross-checks only)."""
+    _lib.check(_lib.load().gsb_set_blend_variant({"native": 0, "standin": 1}[name]), "gsb_set_blend_variant")
+
+
 def set_multistream(enabled: bool) -> None:
     """Run the views of rasterize_views on separate CUDA streams (default) or back to back."""
     global _multistream

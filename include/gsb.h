@@ -190,6 +190,12 @@ int gsb_profile_read(float* ms_out, int* calls_out);
 /* Kernels launched by this library (host-side counter, all threads) since process start. */
 long long gsb_launch_count(void);
 
+/* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
+ *   0  native kernels (the product path);
+ *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
+ *      culling, per-pixel global atomics — for measurement context and as a GPU cross-check only. */
+int gsb_set_blend_variant(int variant);
+
 /* Test / measurement helpers. */
 /* Materialise the sorted 64-bit (tile<<32 | depth bits) key of every instance. */
 int gsb_debug_sorted_keys(int P, int H, int W, const void* saved, const void* scratch,
