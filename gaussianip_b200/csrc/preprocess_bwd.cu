@@ -16,18 +16,23 @@ namespace {
 
 __device__ __forceinline__ void put(float* p, float v, int acc) { *p = acc ? (*p + v) : v; }
 
-struct Accum {            // per-Gaussian gradient sums over the views of one launch
+template <int DEG>
+struct Accum {            // per-Gaussian gradient sums over the views of one launch (registers)
   float dp[3], d2[2], dop, dsc[3], dq[4], dcov[6], dcol[3];
-  float dsh[48];
+  float dsh[3 * (DEG + 1) * (DEG + 1)];
 };
 
 // Adds the contribution of ONE view to the sums in A (Gaussian i is visible in that view).
+// DEG = active SH degree (compile time, so the basis / coefficient loops unroll and the 3(DEG+1)^2
+// SH gradient sums stay in registers); sh = this Gaussian's coefficient row (staged in shared memory).
+template <int DEG>
 __device__ __forceinline__ void
-view_contrib(const View& v, int i, int K, const float* sV, const float* sM, const float* sCam,
+view_contrib(const View& v, int i, const float* sV, const float* sM, const float* sCam,
              const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rots,
-             const float* __restrict__ shs, const float* __restrict__ cov3Dp, const Geom* __restrict__ geom,
-             const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, bool precomp_color, Accum& A) {
-  const int ncoef = (v.sh_degree + 1) * (v.sh_degree + 1);
+             const float* sh, const float* __restrict__ cov3Dp, const Geom* __restrict__ geom,
+             const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, bool precomp_color,
+             Accum<DEG>& A) {
+  constexpr int ncoef = (DEG + 1) * (DEG + 1);
   const float4* gp = reinterpret_cast<const float4*>(ggrad + i);
   const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
   // moments -> gradients of the screen-space mean (NDC units) and of the conic
@@ -55,18 +60,17 @@ view_contrib(const View& v, int i, int K, const float* sV, const float* sM, cons
     const float sum2 = ox * ox + oy * oy + oz * oz;
     const float inv = rsqrtf(sum2);
     const float x = ox * inv, y = oy * inv, z = oz * inv;
-    const float* sh = shs + (size_t)i * K * 3;
     const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
     float basis[16];
     float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
     basis[0] = C0;
-    if (v.sh_degree > 0) {
+    if (DEG > 0) {
       basis[1] = -C1 * y; basis[2] = C1 * z; basis[3] = -C1 * x;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         ddx[c] = -C1 * sh[9 + c]; ddy[c] = -C1 * sh[3 + c]; ddz[c] = C1 * sh[6 + c];
       }
-      if (v.sh_degree > 1) {
+      if (DEG > 1) {
         const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
         const float a0 = 1.0925484305920792f, a1 = -1.0925484305920792f, a2 = 0.31539156525252005f,
                     a3 = -1.0925484305920792f, a4 = 0.5462742152960396f;
@@ -78,7 +82,7 @@ view_contrib(const View& v, int i, int K, const float* sV, const float* sM, cons
           ddy[c] += a0 * x * sh[12 + c] + a1 * z * sh[15 + c] + a2 * (-2.f * y) * sh[18 + c] + a4 * (-2.f * y) * sh[24 + c];
           ddz[c] += a1 * y * sh[15 + c] + a2 * 4.f * z * sh[18 + c] + a3 * x * sh[21 + c];
         }
-        if (v.sh_degree > 2) {
+        if (DEG > 2) {
           const float b0 = -0.5900435899266435f, b1 = 2.890611442640554f, b2 = -0.4570457994644658f,
                       b3 = 0.3731763325901154f, b4 = -0.4570457994644658f, b5 = 1.445305721320277f,
                       b6 = -0.5900435899266435f;
@@ -103,6 +107,7 @@ view_contrib(const View& v, int i, int K, const float* sV, const float* sM, cons
         }
       }
     }
+#pragma unroll
     for (int k = 0; k < ncoef; ++k) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) A.dsh[3 * k + c] += basis[k] * grgb[c];
@@ -244,13 +249,15 @@ view_contrib(const View& v, int i, int K, const float* sV, const float* sM, cons
   }
 }
 
-__global__ void __launch_bounds__(256)
+template <int DEG>
+__global__ void __launch_bounds__(256, 2)
 preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rots,
                       const float* __restrict__ shs, const float* __restrict__ cov3Dp,
                       float* __restrict__ dmeans3D, float* __restrict__ dmeans2D, float* __restrict__ dshs,
                       float* __restrict__ dcolors, float* __restrict__ dopac, float* __restrict__ dscales,
                       float* __restrict__ drots, float* __restrict__ dcov3D, int acc) {
+  constexpr int NC3 = 3 * (DEG + 1) * (DEG + 1);
   __shared__ float sV[GSB_MAX_VIEWS][16], sM[GSB_MAX_VIEWS][16], sCam[GSB_MAX_VIEWS][4];
   for (int t = threadIdx.x; t < B.V * 16; t += blockDim.x) {
     sV[t >> 4][t & 15] = B.a[t >> 4].v.view[t & 15];
@@ -258,53 +265,68 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   }
   for (int t = threadIdx.x; t < B.V * 3; t += blockDim.x) sCam[t / 3][t % 3] = B.a[t / 3].v.campos[t % 3];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  // a Gaussian's coefficient row is K*12 contiguous bytes; the rows of a warp are contiguous too, so
+  // reading one's own row touches every fetched sector completely (re-reads across views hit L1)
+  const float* my_sh = shs ? shs + (size_t)i * K * 3 : nullptr;
 
-  Accum A;
+  if (i < P) {
+    Accum<DEG> A;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { A.dp[k] = 0.f; A.dsc[k] = 0.f; A.dcol[k] = 0.f; }
-  A.d2[0] = A.d2[1] = 0.f; A.dop = 0.f;
+    for (int k = 0; k < 3; ++k) { A.dp[k] = 0.f; A.dsc[k] = 0.f; A.dcol[k] = 0.f; }
+    A.d2[0] = A.d2[1] = 0.f; A.dop = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) A.dq[k] = 0.f;
+    for (int k = 0; k < 4; ++k) A.dq[k] = 0.f;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) A.dcov[k] = 0.f;
-  const int ncoef_max = dshs ? min(K, 16) : 0;
-  for (int k = 0; k < 3 * ncoef_max; ++k) A.dsh[k] = 0.f;
+    for (int k = 0; k < 6; ++k) A.dcov[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NC3; ++k) A.dsh[k] = 0.f;
 
-  for (int vi = 0; vi < B.V; ++vi) {
-    const BwdView& bv = B.a[vi];
-    if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
-    view_contrib(bv.v, i, K, sV[vi], sM[vi], sCam[vi], means3D, scales, rots, shs, cov3Dp, bv.geom, bv.clamped,
-                 bv.ggrad, dcolors != nullptr, A);
-  }
-
-  put(dmeans3D + 3 * i, A.dp[0], acc); put(dmeans3D + 3 * i + 1, A.dp[1], acc); put(dmeans3D + 3 * i + 2, A.dp[2], acc);
-  put(dmeans2D + 3 * i, A.d2[0], acc); put(dmeans2D + 3 * i + 1, A.d2[1], acc);
-  if (!acc) dmeans2D[3 * i + 2] = 0.f;
-  put(dopac + i, A.dop, acc);
-  if (dcolors) {
-    put(dcolors + 3 * i, A.dcol[0], acc); put(dcolors + 3 * i + 1, A.dcol[1], acc); put(dcolors + 3 * i + 2, A.dcol[2], acc);
-  }
-  if (dshs) {
-    float* dsh = dshs + (size_t)i * K * 3;
-    for (int k = 0; k < 3 * K; ++k) {
-      if (k < 3 * ncoef_max) put(dsh + k, A.dsh[k], acc);
-      else if (!acc) dsh[k] = 0.f;
+    for (int vi = 0; vi < B.V; ++vi) {
+      const BwdView& bv = B.a[vi];
+      if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
+      view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], means3D, scales, rots, my_sh, cov3Dp, bv.geom, bv.clamped,
+                        bv.ggrad, dcolors != nullptr, A);
     }
-  }
-  if (cov3Dp) {
-    float* o = dcov3D + 6 * (size_t)i;
+
+    put(dmeans3D + 3 * i, A.dp[0], acc); put(dmeans3D + 3 * i + 1, A.dp[1], acc); put(dmeans3D + 3 * i + 2, A.dp[2], acc);
+    put(dmeans2D + 3 * i, A.d2[0], acc); put(dmeans2D + 3 * i + 1, A.d2[1], acc);
+    if (!acc) dmeans2D[3 * i + 2] = 0.f;
+    put(dopac + i, A.dop, acc);
+    if (dcolors) {
+      put(dcolors + 3 * i, A.dcol[0], acc); put(dcolors + 3 * i + 1, A.dcol[1], acc); put(dcolors + 3 * i + 2, A.dcol[2], acc);
+    }
+    if (cov3Dp) {
+      float* o = dcov3D + 6 * (size_t)i;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) put(o + k, A.dcov[k], acc);
-  } else {
-    put(dscales + 3 * i, A.dsc[0], acc); put(dscales + 3 * i + 1, A.dsc[1], acc); put(dscales + 3 * i + 2, A.dsc[2], acc);
-    float4* o = reinterpret_cast<float4*>(drots) + i;
-    if (acc) {
-      const float4 old = *o;
-      *o = make_float4(old.x + A.dq[0], old.y + A.dq[1], old.z + A.dq[2], old.w + A.dq[3]);
+      for (int k = 0; k < 6; ++k) put(o + k, A.dcov[k], acc);
     } else {
-      *o = make_float4(A.dq[0], A.dq[1], A.dq[2], A.dq[3]);
+      put(dscales + 3 * i, A.dsc[0], acc); put(dscales + 3 * i + 1, A.dsc[1], acc); put(dscales + 3 * i + 2, A.dsc[2], acc);
+      float4* o = reinterpret_cast<float4*>(drots) + i;
+      if (acc) {
+        const float4 old = *o;
+        *o = make_float4(old.x + A.dq[0], old.y + A.dq[1], old.z + A.dq[2], old.w + A.dq[3]);
+      } else {
+        *o = make_float4(A.dq[0], A.dq[1], A.dq[2], A.dq[3]);
+      }
+    }
+    if (dshs) {
+      float* dsh = dshs + (size_t)i * K * 3;
+      if (((K * 3) & 3) == 0) {              // rows are 16 B aligned: vector stores
+#pragma unroll
+        for (int k = 0; k + 3 < NC3; k += 4) {
+          float4* o = reinterpret_cast<float4*>(dsh + k);
+          float4 val = make_float4(A.dsh[k], A.dsh[k + 1], A.dsh[k + 2], A.dsh[k + 3]);
+          if (acc) { const float4 old = *o; val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w; }
+          *o = val;
+        }
+#pragma unroll
+        for (int k = NC3 & ~3; k < NC3; ++k) put(dsh + k, A.dsh[k], acc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NC3; ++k) put(dsh + k, A.dsh[k], acc);
+      }
+      if (!acc) for (int k = NC3; k < 3 * K; ++k) dsh[k] = 0.f;   // coefficients above the active degree
     }
   }
 }
@@ -318,10 +340,37 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
                           cudaStream_t st) {
   if (P == 0) return GSB_OK;
   if (B.V < 1 || B.V > GSB_MAX_VIEWS) return GSB_E_INVALID;
-  preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(B, P, K, means3D, scales, rots, shs, cov3D, dmeans3D,
-                                                         dmeans2D, shs ? dshs : nullptr,
-                                                         colors ? dcolors : nullptr, dopac, dscales, drots, dcov3D,
-                                                         accumulate);
+  const int deg = B.a[0].v.sh_degree;
+  for (int v = 1; v < B.V; ++v)
+    if (B.a[v].v.sh_degree != deg) return GSB_E_INVALID;   // one degree per launch
+  const int nc3 = 3 * (deg + 1) * (deg + 1);
+  const size_t smem = 0;
+  (void)nc3;
+  const int grid = (P + 255) / 256;
+#define GSB_LAUNCH_BWD(D)                                                                                       \
+  do {                                                                                                          \
+    if (smem > 48 * 1024) {                                                                                     \
+      static bool configured[64] = {};                                                                          \
+      int dev = 0;                                                                                              \
+      GSB_CUDA(cudaGetDevice(&dev));                                                                            \
+      if (!configured[dev & 63]) {                                                                              \
+        GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      64 * 1024));                                                              \
+        configured[dev & 63] = true;                                                                            \
+      }                                                                                                         \
+    }                                                                                                           \
+    preprocess_bwd_kernel<D><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D, dmeans3D,     \
+                                                      dmeans2D, shs ? dshs : nullptr, colors ? dcolors : nullptr, \
+                                                      dopac, dscales, drots, dcov3D, accumulate);                \
+  } while (0)
+  switch (shs ? deg : 0) {
+    case 0: GSB_LAUNCH_BWD(0); break;
+    case 1: GSB_LAUNCH_BWD(1); break;
+    case 2: GSB_LAUNCH_BWD(2); break;
+    case 3: GSB_LAUNCH_BWD(3); break;
+    default: return GSB_E_INVALID;
+  }
+#undef GSB_LAUNCH_BWD
   GSB_POST_LAUNCH(debug, st, "preprocess_bwd_kernel");
   return GSB_OK;
 }
