@@ -421,6 +421,11 @@ def main():
                 "secondary": {"bound": "instruction issue (not HBM): ncu 2.9-3.1 of 4 inst/cycle while active",
                               "pair_evals_upper_bound_per_s": 256 * D / (stage_ms[dom] * 1e-3)
                               if stage_ms[dom] > 0 else None},
+                "sort": {"depth_sort_keys_per_s": (P * 4 / (stage_ms["depth_sort"] * 1e-3)) if stage_ms["depth_sort"] > 0 else None,
+                         "tile_sort_keys_per_s": (D * 2 / (stage_ms["tile_sort"] * 1e-3)) if stage_ms["tile_sort"] > 0 else None,
+                         "note": "keys x 8-bit passes per second: 32-bit depth keys of the P Gaussians (4 passes) and "
+                                 "tile ids of the D instances (2 passes at 4096 tiles); same final order as one "
+                                 "64-bit (tile|depth) sort of D keys"},
                 "stage_us_per_view": {k: round(v * 1e3, 1) for k, v in stage_ms.items()},
                 "stage_us_per_view_overlapped": {k: round(m / c * 1e3, 1) if c else 0.0 for k, (m, c) in prof_conc.items()},
                 "note": "avg_launch_ms / stage_us_per_view: CUDA events inside bench.py on a serialised pass of the same "
