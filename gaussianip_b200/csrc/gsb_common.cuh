@@ -135,6 +135,11 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
                           float* dscales, float* drots, float* dcov3D, int accumulate, bool debug,
                           cudaStream_t st);
 
+int launch_adam_stats(int G, float* const* p, const float* const* g, float* const* m, float* const* v,
+                      const long long* n, const float* lr, float beta1, float beta2, float eps, long long step,
+                      float grad_scale, long long stats_n, const float* viewspace_grad, const int32_t* radii,
+                      float* xyz_gradient_accum, float* denom, float* max_radii2D, cudaStream_t st);
+
 // radix sort (binning.cu)
 size_t radix_tmp_bytes(long long n_cap);
 template <typename KeyT>

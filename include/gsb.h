@@ -190,6 +190,18 @@ int gsb_profile_read(float* ms_out, int* calls_out);
 /* Kernels launched by this library (host-side counter, all threads) since process start. */
 long long gsb_launch_count(void);
 
+/* the step after the hot path — torch.optim.Adam over up to GSB_ADAM_MAX_GROUPS
+ * parameter tensors (gaussian_model.py:138-159: six groups, own lr each, eps 1e-15) plus the
+ * densification statistics (GaussianIP.py:456-457, gaussian_model.py:420-422) in ONE kernel.
+ * `step` is the 1-based Adam step count; grad_scale multiplies every gradient first (AMP unscale, 1 = off);
+ * stats_n = 0 skips the statistics.  Pointer arrays are HOST arrays of DEVICE pointers. */
+#define GSB_ADAM_MAX_GROUPS 8
+int gsb_adam_step(int n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const long long* counts, const float* lrs, float beta1, float beta2,
+                  float eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
+                  const int32_t* radii, float* xyz_gradient_accum, float* denom, float* max_radii2D,
+                  void* stream);
+
 /* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
  *   0  native kernels (the product path);
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
