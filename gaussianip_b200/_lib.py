@@ -56,7 +56,7 @@ _PROTOS = {
     "gsb_profile_enable": (C.c_int, [C.c_int]),
     "gsb_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "gsb_launch_count": (C.c_longlong, []),
-    "gsb_adam_step": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_longlong,
+    "gsb_adam_step": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_longlong,
                                 C.c_float, C.c_longlong, _P, _P, _P, _P, _P, _P]),
     "gsb_set_blend_variant": (C.c_int, [C.c_int]),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),

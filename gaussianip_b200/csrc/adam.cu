@@ -21,6 +21,7 @@ struct AdamBatch {
   long long first_block[GSB_ADAM_MAX_GROUPS + 1];   // blocks of group k: [first_block[k], first_block[k+1])
   float step_size[GSB_ADAM_MAX_GROUPS];              // lr / (1 - beta1^t)
   float beta1, beta2, eps, bc2_sqrt, grad_scale;     // grad_scale multiplies g first (AMP unscale), 1 = off
+  float omb1, omb2;                                  // 1 - beta, rounded from double as torch does
   // densification statistics (optional, stats_n = 0 disables): one extra range of blocks
   long long stats_n;
   const float* viewspace_grad;   // [P,3] summed over views (and ranks)
@@ -36,8 +37,8 @@ constexpr int ADAM_PER_BLOCK = ADAM_THREADS * ADAM_VEC;
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float step_size, const AdamBatch& B) {
   g *= B.grad_scale;
-  m = m + (g - m) * (1.0f - B.beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * B.beta2 + (1.0f - B.beta2) * g * g;               // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+  m = m + (g - m) * B.omb1;                                 // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * B.beta2 + B.omb2 * g * g;                         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
   const float denom = sqrtf(v) / B.bc2_sqrt + B.eps;
   p = p - step_size * (m / denom);                          // param.addcdiv_(exp_avg, denom, -step_size)
 }
@@ -86,15 +87,15 @@ adam_stats_kernel(AdamBatch B) {
 }  // namespace
 
 int launch_adam_stats(int G, float* const* p, const float* const* g, float* const* m, float* const* v,
-                      const long long* n, const float* lr, float beta1, float beta2, float eps, long long step,
+                      const long long* n, const float* lr, double beta1, double beta2, double eps, long long step,
                       float grad_scale, long long stats_n, const float* viewspace_grad, const int32_t* radii,
                       float* xyz_gradient_accum, float* denom, float* max_radii2D, cudaStream_t st) {
   if (G < 0 || G > GSB_ADAM_MAX_GROUPS || step < 1) return GSB_E_INVALID;
   AdamBatch B;
   B.G = G;
   long long blocks = 0;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   for (int k = 0; k < G; ++k) {
     if (n[k] < 0 || (n[k] > 0 && (!p[k] || !g[k] || !m[k] || !v[k]))) return GSB_E_INVALID;
     B.p[k] = p[k]; B.g[k] = g[k]; B.m[k] = m[k]; B.v[k] = v[k]; B.n[k] = n[k];
@@ -103,7 +104,8 @@ int launch_adam_stats(int G, float* const* p, const float* const* g, float* cons
     B.step_size[k] = (float)((double)lr[k] / bc1);
   }
   for (int k = G; k <= GSB_ADAM_MAX_GROUPS; ++k) B.first_block[k] = blocks;
-  B.beta1 = beta1; B.beta2 = beta2; B.eps = eps; B.bc2_sqrt = (float)sqrt(bc2); B.grad_scale = grad_scale;
+  B.omb1 = (float)(1.0 - beta1); B.omb2 = (float)(1.0 - beta2);
+  B.beta1 = (float)beta1; B.beta2 = (float)beta2; B.eps = (float)eps; B.bc2_sqrt = (float)sqrt(bc2); B.grad_scale = grad_scale;
   B.stats_n = stats_n;
   B.viewspace_grad = viewspace_grad; B.radii = radii; B.xyz_gradient_accum = xyz_gradient_accum;
   B.denom = denom; B.max_radii2D = max_radii2D;

@@ -153,8 +153,8 @@ int gsb_profile_read(float* ms_out, int* calls_out) {
 long long gsb_launch_count(void) { return g_launches.load(); }
 
 int gsb_adam_step(int n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
-                  float* const* exp_avg_sq, const long long* counts, const float* lrs, float beta1, float beta2,
-                  float eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
+                  float* const* exp_avg_sq, const long long* counts, const float* lrs, double beta1, double beta2,
+                  double eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
                   const int32_t* radii, float* xyz_gradient_accum, float* denom, float* max_radii2D,
                   void* stream) {
   if (n_groups > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !counts || !lrs)) return GSB_E_INVALID;

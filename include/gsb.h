@@ -197,8 +197,8 @@ long long gsb_launch_count(void);
  * stats_n = 0 skips the statistics.  Pointer arrays are HOST arrays of DEVICE pointers. */
 #define GSB_ADAM_MAX_GROUPS 8
 int gsb_adam_step(int n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
-                  float* const* exp_avg_sq, const long long* counts, const float* lrs, float beta1, float beta2,
-                  float eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
+                  float* const* exp_avg_sq, const long long* counts, const float* lrs, double beta1, double beta2,
+                  double eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
                   const int32_t* radii, float* xyz_gradient_accum, float* denom, float* max_radii2D,
                   void* stream);
 
