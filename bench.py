@@ -148,24 +148,32 @@ def cpu_reference_run(a, steps, warmup, budget_s):
         frac = float((rng[:, 1] - rng[:, 0])[sel.numpy()].sum()) / max(1, len(binning.keys))
         return dt, frac
 
-    # probe with a sparse sample to size the real one
-    stride = max(1, tile_rows_total // 4)
-    dt, frac = one(0, stride, 0)
-    est_full = dt / max(frac, 1e-6) * 0.9
+    # Calibration: t_step = t_const + t_var * frac, where t_const is the per-view work that does not
+    # shrink with the tile sample (projection, binning and their backward over all Gaussians) and
+    # frac the blended share of the view's instances.  Two probes with different strides give both.
+    sa, sb = max(2, tile_rows_total // 4), max(1, tile_rows_total // 8)
+    ta, fa = one(0, sa, 0)
+    tb, fb = one(0, sb, 0)
+    t_var = max(1e-6, (tb - ta) / max(fb - fa, 1e-6))
+    t_const = min(max(0.0, ta - t_var * fa), ta)
+    est_full = t_const + t_var
     per_step_budget = budget_s / max(1, steps + warmup)
     stride = 1
-    while stride < tile_rows_total and est_full / stride > per_step_budget:
+    while stride < tile_rows_total and t_const + t_var / stride > per_step_budget:
         stride *= 2
-    times, fracs = [], []
+    times, fulls, fracs = [], [], []
     for i in range(warmup + steps):
         dt, frac = one(i, stride, i % stride)
         if i >= warmup:
             times.append(dt); fracs.append(frac)
-    vps = sum(fracs) / sum(times)
+            fulls.append(t_const + max(0.0, dt - t_const) / max(frac, 1e-6) if stride > 1 else dt)
+    vps = len(fulls) / sum(fulls)
     sample = (f"{steps} steps x 1 view: full preprocess+binning of {a.points} Gaussians, blend+backward of every "
               f"{stride}-th tile row ({100 * sum(fracs) / len(fracs):.1f}% of the view's instances per step), "
-              f"{sum(times):.1f} s CPU wall; views/s = blended instance fraction / time")
-    return vps, cores, sample, sum(times) / len(times) * 1e3
+              f"{sum(times):.1f} s CPU wall; full-view time per step = t_const + (t_step - t_const) / blended fraction "
+              f"with t_const = {t_const:.2f} s from a two-stride calibration (estimated full view {est_full:.1f} s); "
+              f"views/s = steps / sum of full-view times")
+    return vps, cores, sample, sum(fulls) / len(fulls) * 1e3
 
 
 # ---- our arm -----------------------------------------------------------------------------------------------
