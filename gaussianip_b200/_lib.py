@@ -60,6 +60,8 @@ _PROTOS = {
                                 C.c_float, C.c_longlong, _P, _P, _P, _P, _P, _P]),
     "gsb_set_blend_variant": (C.c_int, [C.c_int]),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
+    "gsb_knn_scratch_bytes": (C.c_size_t, [C.c_longlong]),
+    "gsb_knn_dist2": (C.c_int, [C.c_longlong, _P, _P, _P, C.c_size_t, _P]),
     "gsb_debug_sorted_keys": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.c_longlong, _P, _P]),
     "gsb_radix_tmp_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
     "gsb_radix_sort_pairs_u32": (C.c_int, [C.c_longlong, _P, _P, _P, _P, C.c_int, _P, _P]),

@@ -341,6 +341,14 @@ int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix, const
   return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 }
 
+size_t gsb_knn_scratch_bytes(long long P) { return knn_scratch_bytes(P); }
+
+int gsb_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,
+                  void* stream) {
+  if (P < 0) return GSB_E_INVALID;
+  return launch_knn_dist2(P, points, mean_dist2, scratch, scratch_bytes, false, (cudaStream_t)stream);
+}
+
 int gsb_debug_sorted_keys(int P, int H, int W, const void* saved, const void* scratch, long long D_cap,
                           uint64_t* keys_out, void* stream) {
   if (!saved || !scratch || !keys_out) return GSB_E_INVALID;

@@ -153,5 +153,9 @@ int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void
                              long long D_cap, uint64_t* keys_out, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
 int radix_num_passes(int end_bit);
+// 3-NN mean distance (knn.cu)
+size_t knn_scratch_bytes(long long P);
+int launch_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,
+                     bool debug, cudaStream_t st);
 
 }  // namespace gsb

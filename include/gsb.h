@@ -202,6 +202,15 @@ int gsb_adam_step(int n_groups, float* const* params, const float* const* grads,
                   const int32_t* radii, float* xyz_gradient_accum, float* denom, float* max_radii2D,
                   void* stream);
 
+/* replaces `simple_knn._C.distCUDA2` (simple-knn/spatial.cu:15-26 -> SimpleKNN::knn,
+ * simple_knn.cu:186-221; callers gaussian_model.py:123, gs_renderer.py:387): mean_dist2[i] = mean of the
+ * squared distances from point i to its 3 nearest other points, in the reference's own fp32 rounding
+ * (bit-identical output).  points: [P,3] fp32 device, mean_dist2: [P] fp32 device, scratch: device,
+ * >= gsb_knn_scratch_bytes(P).  Asynchronous on `stream`; no host read-back. */
+size_t gsb_knn_scratch_bytes(long long P);
+int gsb_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch,
+                  size_t scratch_bytes, void* stream);
+
 /* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
  *   0  native kernels (the product path);
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
