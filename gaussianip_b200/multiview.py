@@ -116,19 +116,37 @@ class ViewParallel:
         self.bucket = GradBucket(params, n_points)
         self.n_points = n_points
 
+    def _attempt(self, body: Callable):
+        """Run one whole step speculatively (rasterizer.speculation): the forwards inside do not stall
+        the host on the per-view instance count; if a view turns out not to have fitted its capacity the
+        step's results are discarded and the step is run again with the raised capacity.  Local only —
+        there is no collective inside, so ranks need not agree on the number of attempts."""
+        from . import rasterizer
+        for _ in range(8):
+            with rasterizer.speculation() as spec:
+                result = body()
+            if spec.validate():
+                return result
+        raise RuntimeError("instance capacity overflowed on 8 consecutive attempts")
+
     def step(self, n_views: int, render_fn: Callable, loss_fn: Callable, views: Optional[Sequence[int]] = None):
         b = self.bucket
-        b.zero_()
-        b.attach()
         local = shard_views(n_views, self.rank, self.world) if views is None else list(views)
-        radii = torch.zeros(self.n_points, dtype=torch.int32, device=b.device)
-        total = torch.zeros((), dtype=torch.float32, device=b.device)
-        for v in local:
-            out = render_fn(v, b.viewspace_points)
-            radii = torch.maximum(radii, out["radii"])
-            loss = loss_fn(v, out)
-            loss.backward()            # accumulates into the bucket views, view after view
-            total = total + loss.detach()
+
+        def body():
+            b.zero_()
+            b.attach()
+            radii = torch.zeros(self.n_points, dtype=torch.int32, device=b.device)
+            total = torch.zeros((), dtype=torch.float32, device=b.device)
+            for v in local:
+                out = render_fn(v, b.viewspace_points)
+                radii = torch.maximum(radii, out["radii"])
+                loss = loss_fn(v, out)
+                loss.backward()            # accumulates into the bucket views, view after view
+                total = total + loss.detach()
+            return radii, total
+
+        radii, total = self._attempt(body)
         b.all_reduce(self.group)
         all_reduce_radii_max(radii, self.group)
         if self.world > 1:
@@ -141,18 +159,20 @@ class ViewParallel:
         render_views_fn(local_view_indices, viewspace_points) -> dict with 'radii' (max over the
         local views) and stacked outputs; loss_fn(local_view_indices, dict) -> scalar."""
         b = self.bucket
-        b.zero_()
-        b.attach()
         local = shard_views(n_views, self.rank, self.world) if views is None else list(views)
-        if local:
+
+        def body():
+            b.zero_()
+            b.attach()
+            if not local:
+                return (torch.zeros(self.n_points, dtype=torch.int32, device=b.device),
+                        torch.zeros((), dtype=torch.float32, device=b.device))
             out = render_views_fn(local, b.viewspace_points)
-            radii = out["radii"]
             loss = loss_fn(local, out)
             loss.backward()
-            total = loss.detach().to(torch.float32)
-        else:
-            radii = torch.zeros(self.n_points, dtype=torch.int32, device=b.device)
-            total = torch.zeros((), dtype=torch.float32, device=b.device)
+            return out["radii"], loss.detach().to(torch.float32)
+
+        radii, total = self._attempt(body)
         b.all_reduce(self.group)
         all_reduce_radii_max(radii, self.group)
         if self.world > 1:

@@ -25,6 +25,7 @@ Differences from the external operator, by design (B200-first):
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -63,6 +64,7 @@ class _Workspace:
         self.binning_mode = _lib.BIN_TWO_LEVEL
         self.last_num_rendered = 0
         self.retries = 0
+        self.pending = None            # speculative forward whose counts were not read yet
 
     def capacity_for(self, P: int) -> int:
         if self.d_cap == 0:
@@ -202,6 +204,8 @@ class _ForwardCall:
                     self.alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
                     self.radii = torch.empty(P, dtype=torch.int32, device=device)
             ws = self.ws
+            if ws.pending is not None and ws.pending is not self:
+                ws.pending.settle()         # its counts buffer is about to be reused
             self.d_cap = ws.capacity_for(P)
             self.L = _lib.layout(P, H, W, self.d_cap)
             self.scratch = ws.ensure_scratch(self.L.scratch_bytes)
@@ -214,8 +218,33 @@ class _ForwardCall:
             _lib.check(rc, "gsb_forward")
         return self
 
+    def _account(self, D: int) -> None:
+        ws, P = self.ws, self.P
+        ws.last_num_rendered = D
+        _stats["num_rendered"] = D
+        _stats["views"] += 1
+        _stats["num_rendered_sum"] += D
+        # follow the scene downwards slowly so one huge view does not pin memory forever
+        if D * 4 < ws.d_cap and ws.d_cap > max(1 << 16, 4 * P):
+            ws.d_cap = max(1 << 16, 4 * P, 2 * D)
+
+    def _saved(self, D) -> "_Saved":
+        sv = _Saved()
+        sv.block, sv.layout, sv.d_cap, sv.P, sv.K, sv.H, sv.W = self.block, self.L, self.d_cap, self.P, self.K, self.H, self.W
+        sv.num_rendered, sv.scratch, sv.settings_keep = D, self.scratch, self.keep
+        return sv
+
     def finish(self):
         ws, P = self.ws, self.P
+        spec = _active_speculation()
+        if spec is not None:
+            # whole-step speculation (see `speculation`): do not wait for the counts now; the
+            # owner of the step validates them after everything is enqueued and redoes the step
+            # if this view did not fit
+            self.sv = self._saved(None)
+            ws.pending = self
+            spec.calls.append(self)
+            return self.color, self.radii, self.depth, self.alpha, self.sv
         while True:
             ws.event.synchronize()          # waits for the 32-byte counts copy only
             D = int(ws.host_counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
@@ -225,17 +254,63 @@ class _ForwardCall:
             ws.retries += 1
             with torch.cuda.stream(self.stream):
                 self.enqueue()
-        ws.last_num_rendered = D
-        _stats["num_rendered"] = D
-        _stats["views"] += 1
-        _stats["num_rendered_sum"] += D
-        # follow the scene downwards slowly so one huge view does not pin memory forever
-        if D * 4 < ws.d_cap and ws.d_cap > max(1 << 16, 4 * P):
-            ws.d_cap = max(1 << 16, 4 * P, 2 * D)
-        sv = _Saved()
-        sv.block, sv.layout, sv.d_cap, sv.P, sv.K, sv.H, sv.W = self.block, self.L, self.d_cap, P, self.K, self.H, self.W
-        sv.num_rendered, sv.scratch, sv.settings_keep = D, self.scratch, self.keep
-        return self.color, self.radii, self.depth, self.alpha, sv
+        self._account(D)
+        return self.color, self.radii, self.depth, self.alpha, self._saved(D)
+
+    def settle(self) -> bool:
+        """Speculative call: read the counts (they were produced long ago on the device timeline).
+        Returns False if the view overflowed its instance capacity; the capacity is then raised
+        for the next attempt."""
+        ws, P = self.ws, self.P
+        if ws.pending is not self:
+            return self.fits
+        ws.event.synchronize()
+        D = int(ws.host_counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
+        ws.pending = None
+        self.fits = D <= self.d_cap
+        if self.fits:
+            self.sv.num_rendered = D
+            self._account(D)
+        else:
+            ws.d_cap = int(D * 1.25) + 4096
+            ws.retries += 1
+        return self.fits
+
+
+class speculation:
+    """Context for callers that own a WHOLE step (forward of all views, loss, backward) and can
+    redo it: inside, forwards do not block the host on the 32-byte instance count; afterwards
+    ``validate()`` reads the counts and reports whether every view fitted its capacity.  On False
+    the capacities have been raised and the caller must discard the step's results and run it
+    again (gaussianip_b200.multiview.ViewParallel does).  Removes the one host stall per step
+    that otherwise lets the GPU run dry between the forward and the backward."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __enter__(self):
+        if getattr(_tls, "spec", None) is not None:
+            raise RuntimeError("speculation contexts do not nest")
+        _tls.spec = self
+        return self
+
+    def __exit__(self, *exc):
+        _tls.spec = None
+        return False
+
+    def validate(self) -> bool:
+        ok = True
+        for call in self.calls:
+            ok = call.settle() and ok
+        self.calls = []
+        return ok
+
+
+_tls = threading.local()
+
+
+def _active_speculation():
+    return getattr(_tls, "spec", None)
 
 
 def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):

@@ -342,3 +342,57 @@ def test_native_blend_equals_unculled_standin(cuda_device, name):
     for k, g in ref["grads"].items():
         if g is not None:
             _grad_close(k, got["grads"][k], g, rtol=5e-5)
+
+
+def test_speculative_step_redoes_on_overflow(cuda_device):
+    """ViewParallel runs the whole step without stalling on the instance counts; a view that did not fit
+    its capacity makes the step run again, and the result equals the blocking path's."""
+    from gaussianip_b200 import multiview, rasterizer as R, synthetic
+    dev = cuda_device
+    H = W = 128
+    scene = util.humanoid_scene(P=20000, H=H, W=W, sh_degree=0, scale_boost=10.0)
+    cams = synthetic.ahds_cameras(3, H, W, seed=4, device=dev)
+    g = torch.Generator().manual_seed(8)
+    wc, wd, wa = (torch.randn(3, c, H, W, generator=g).to(dev) for c in (3, 1, 1))
+
+    def settings(views):
+        return [R.GaussianRasterizationSettings(H, W, cams[v].tanfovx, cams[v].tanfovy, scene.bg.to(dev), 1.0,
+                                                cams[v].world_view_transform, cams[v].full_proj_transform, 0,
+                                                cams[v].camera_center, False, False) for v in views]
+
+    def run(shrink):
+        d = scene.inputs(dev, requires_grad=True)
+        params = {k: d[k] for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        vp = multiview.ViewParallel(params, d["means3D"].shape[0])
+
+        def render_views_fn(views, vsp):
+            color, radii, depth, alpha = R.rasterize_views(settings(views), means3D=d["means3D"], means2D=vsp,
+                                                           shs=d["shs"], opacities=d["opacities"],
+                                                           scales=d["scales"], rotations=d["rotations"])
+            return {"render": color, "radii": radii.max(dim=0).values, "depth_3dgs": depth, "alpha_3dgs": alpha}
+
+        def loss_fn(views, out):
+            return (out["render"] * wc).sum() + (out["depth_3dgs"] * wd).sum() + (out["alpha_3dgs"] * wa).sum()
+
+        if shrink:
+            for st in R._streams_for(dev, 3):
+                with torch.cuda.stream(st):
+                    R._workspace(dev).d_cap = 1 << 16
+        retries0 = sum(w.retries for w in R._workspaces.values())
+        out = vp.step_batched(3, render_views_fn, loss_fn, views=range(3))
+        torch.cuda.synchronize()
+        retries = sum(w.retries for w in R._workspaces.values()) - retries0
+        return out, {k: v.grad.clone() for k, v in params.items()}, vp.bucket.viewspace_grad().clone(), retries
+
+    out_a, grads_a, vs_a, _ = run(False)
+    out_b, grads_b, vs_b, retries = run(True)
+    assert retries >= 1, "the shrunken capacity should have overflowed"
+    assert torch.equal(out_a["radii"], out_b["radii"])
+    assert abs(out_a["loss"].item() - out_b["loss"].item()) <= 1e-5 * abs(out_a["loss"].item())
+    for k in grads_a:
+        _grad_close(k, grads_b[k], grads_a[k], rtol=2e-5)
+    _grad_close("viewspace", vs_b, vs_a, rtol=2e-5)
+    # nothing is left pending, and the blocking path still works afterwards
+    assert all(w.pending is None for w in R._workspaces.values())
+    got = util.run_gpu(scene, dev)
+    assert (got["color"].cpu() - util.run_oracle(scene)["color"]).abs().max().item() <= FWD_ATOL
