@@ -60,6 +60,9 @@ _PROTOS = {
                                 C.c_float, C.c_longlong, _P, _P, _P, _P, _P, _P]),
     "gsb_set_blend_variant": (C.c_int, [C.c_int]),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
+    "gsb_mask_index_tmp_bytes": (C.c_size_t, [C.c_longlong]),
+    "gsb_mask_to_index": (C.c_int, [C.c_longlong, _P, _P, _P, _P, _P]),
+    "gsb_gather_rows": (C.c_int, [C.c_int, _P, _P, _P, C.c_longlong, _P, C.c_longlong, _P]),
     "gsb_knn_scratch_bytes": (C.c_size_t, [C.c_longlong]),
     "gsb_knn_dist2": (C.c_int, [C.c_longlong, _P, _P, _P, C.c_size_t, _P]),
     "gsb_debug_sorted_keys": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.c_longlong, _P, _P]),
@@ -125,3 +128,4 @@ def profile_read():
 
 def launch_count() -> int:
     return int(load().gsb_launch_count())
+GATHER_MAX_TENSORS = 24

@@ -24,7 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(ROO
 # preprocess.cu must not contract a*b+c into FMA: the CPU oracle rounds every op separately.
 PER_FILE = {"preprocess.cu": ["-fmad=false"]}
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "preprocess_bwd.cu",
-           "standin.cu", "adam.cu", "knn.cu"]
+           "standin.cu", "adam.cu", "knn.cu", "compact.cu"]
 
 
 def _nvcc() -> str:

@@ -341,6 +341,20 @@ int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix, const
   return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 }
 
+size_t gsb_mask_index_tmp_bytes(long long n) { return mask_index_tmp_bytes(n); }
+
+int gsb_mask_to_index(long long n, const uint8_t* mask, int64_t* index, uint32_t* count, void* tmp, void* stream) {
+  if (n < 0 || !count || (n > 0 && (!mask || !index || !tmp))) return GSB_E_INVALID;
+  return launch_mask_to_index(n, mask, index, count, tmp, (cudaStream_t)stream);
+}
+
+int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, const int* widths, long long n_rows,
+                    const int64_t* index, long long dst_row0, void* stream) {
+  if (n_tensors < 0 || n_rows < 0 || dst_row0 < 0) return GSB_E_INVALID;
+  if (n_tensors > 0 && (!src || !dst || !widths)) return GSB_E_INVALID;
+  return launch_gather_rows(n_tensors, src, dst, widths, n_rows, index, dst_row0, (cudaStream_t)stream);
+}
+
 size_t gsb_knn_scratch_bytes(long long P) { return knn_scratch_bytes(P); }
 
 int gsb_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,

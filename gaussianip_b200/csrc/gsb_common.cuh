@@ -153,6 +153,11 @@ int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void
                              long long D_cap, uint64_t* keys_out, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
 int radix_num_passes(int end_bit);
+// densify/prune data movement (compact.cu)
+size_t mask_index_tmp_bytes(long long n);
+int launch_mask_to_index(long long n, const uint8_t* mask, int64_t* index, uint32_t* count, void* tmp, cudaStream_t st);
+int launch_gather_rows(int n_tensors, const float* const* src, float* const* dst, const int* widths, long long n_rows,
+                       const int64_t* index, long long dst_row0, cudaStream_t st);
 // 3-NN mean distance (knn.cu)
 size_t knn_scratch_bytes(long long P);
 int launch_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,

@@ -211,6 +211,19 @@ size_t gsb_knn_scratch_bytes(long long P);
 int gsb_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch,
                   size_t scratch_bytes, void* stream);
 
+/* data movement of densify / clone / split / prune (gaussian_model.py:281-418).
+ * gsb_mask_to_index: stable stream compaction — index[0..count) = positions of the non-zero mask bytes in
+ *   ascending order (what `tensor[mask]` / torch.nonzero use), count[0] = how many; device-side, asynchronous.
+ *   tmp: device, >= gsb_mask_index_tmp_bytes(n).
+ * gsb_gather_rows: ONE launch for up to GSB_GATHER_MAX_TENSORS row-major fp32 tensors sharing the row index:
+ *   dst[t][dst_row0 + r][:] = src[t][index ? index[r] : r][:] for r < n_rows, or zeros where src[t] == NULL
+ *   (new points' Adam moments, cat_tensors_to_optimizer :334-335).  src/dst/widths are HOST arrays; widths in floats. */
+#define GSB_GATHER_MAX_TENSORS 24
+size_t gsb_mask_index_tmp_bytes(long long n);
+int gsb_mask_to_index(long long n, const uint8_t* mask, int64_t* index, uint32_t* count, void* tmp, void* stream);
+int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, const int* widths,
+                    long long n_rows, const int64_t* index, long long dst_row0, void* stream);
+
 /* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
  *   0  native kernels (the product path);
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
