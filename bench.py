@@ -48,6 +48,13 @@ def parse():
     ap.add_argument("--variant", default="native", choices=["native", "standin"],
                     help="standin = reference-STRUCTURE kernels of csrc/standin.cu + 64-bit key sort + per-view "
                          "Python loop, for context only (never the reference, never the product)")
+    ap.add_argument("--view-sharding", default="interleaved", choices=["balanced", "interleaved"],
+                    help="N>1: how the step's world x views cameras are dealt to the ranks")
+    ap.add_argument("--exchange-algo", default="auto", choices=["auto", "push_all", "owner_push"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "fused"],
+                    help="N>1: all-reduce the gradient bucket with NCCL, or reduce inside the backward kernel "
+                         "over NVLink peer / NVLS multicast memory (gaussianip_b200/exchange.py); auto = fused "
+                         "when every rank can map multicast memory, else NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -231,16 +238,24 @@ def main():
         get_scaling = property(lambda s: torch.exp(s.p["scaling"]))
         get_rotation = property(lambda s: torch.nn.functional.normalize(s.p["rotation"]))
 
-    rng = np.random.default_rng(1000 + rank)
+    # The step's GLOBAL batch of views (world x views-per-GPU random orbit cameras) is sampled identically on
+    # every rank (common seed); each rank then takes its share: cost-balanced (default) or interleaved.
+    rng = np.random.default_rng(1000)
+    n_global = a.views * world
 
     def sample_cameras_host():
-        """camera_data.py:349-364 distributions; returns (c2w, fovy) per view, host side."""
-        out = []
-        for i in range(a.views):
-            az = (rng.random() + i) / a.views * 360.0 - 180.0
-            out.append((look_at_c2w(orbit_position(az, rng.uniform(-30, 30), rng.uniform(1.3, 1.7))),
-                        float(np.radians(rng.uniform(40, 70)))))
-        return out
+        """camera_data.py:349-364 distributions; returns this rank's (c2w, fovy) per view, host side."""
+        specs, costs = [], []
+        for i in range(n_global):
+            az = (rng.random() + i) / n_global * 360.0 - 180.0
+            el, dist_, fovy = rng.uniform(-30, 30), rng.uniform(1.3, 1.7), float(np.radians(rng.uniform(40, 70)))
+            specs.append((look_at_c2w(orbit_position(az, el, dist_)), fovy))
+            costs.append(multiview.view_cost_proxy(dist_, fovy))
+        if a.view_sharding == "balanced":
+            mine = multiview.shard_views_balanced(costs, rank, world)
+        else:
+            mine = multiview.shard_views(n_global, rank, world)
+        return [specs[v] for v in mine]
 
     total_steps = a.warmup + a.steps
     cam_specs = [sample_cameras_host() for _ in range(total_steps)]
@@ -249,7 +264,14 @@ def main():
     bg = torch.zeros(3, device=dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    vp = multiview.ViewParallel(params, a.points)
+    fused = world > 1 and a.exchange in ("auto", "fused")
+    if fused:
+        from gaussianip_b200.exchange import GradExchange
+        if not GradExchange.available(dev):
+            if a.exchange == "fused":
+                raise SystemExit("--exchange fused: NVLS multicast symmetric memory is not available on this box")
+            fused = False
+    vp = multiview.ViewParallel(params, a.points, fused_exchange=fused, exchange_algorithm=a.exchange_algo)
     model = Model(params)
     standin = a.variant == "standin"
     if standin:
@@ -279,8 +301,9 @@ def main():
                            loss_one, views=range(a.views))
         # public API: all views of the step in one batched render call (same kernels per view as
         # the single-view operator; activations evaluated once per step, one autograd node)
-        def render_views_fn(views, vsp):
-            return renderer.render_views([cams[v] for v in views], model, None, bg, screenspace_points=vsp)
+        def render_views_fn(views, vsp, exchange=None):
+            return renderer.render_views([cams[v] for v in views], model, None, bg, screenspace_points=vsp,
+                                         exchange=exchange)
         return vp.step_batched(a.views, render_views_fn, loss_of, views=range(a.views))
 
     def device_cams(step_idx):
@@ -306,10 +329,13 @@ def main():
         clocks.start()
     barrier()
     t_wall0 = time.perf_counter()
+    host_s = 0.0
     for k in range(a.steps):
         flush_buf.fill_(k & 0xFF)               # L2 flush between timed steps (outside the event pair)
         ev[k][0].record()
+        t_h = time.perf_counter()
         run_step(a.warmup + k, cams_all[a.warmup + k])
+        host_s += time.perf_counter() - t_h     # host time to ENQUEUE the step (includes any host-side waits)
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -453,9 +479,15 @@ def main():
             "config": {"workload": workload_name(a), "points": a.points, "resolution": a.res,
                        "views_per_step_per_gpu": a.views, "sh_degree": a.sh_degree, "num_rendered_D": D,
                        "l2": "256 MiB flush write between timed steps (outside the event pairs)",
-                       "parallelism": f"view-sharded dp{world}, NCCL all-reduce of the flat gradient bucket "
-                                      f"({vp.bucket.nbytes() >> 20} MiB) + radii max per step" if world > 1 else "single GPU",
-                       "wall_s_timed_region": t_wall},
+                       "view_sharding": "n/a" if world == 1 else a.view_sharding,
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"view-sharded dp{world}, gradients reduced INSIDE the backward kernel "
+                                       f"({vp.exchange.algorithm} over NVLink peer / NVLS multicast memory, {vp.exchange.nbytes() >> 20} MiB) "
+                                       f"+ NCCL radii max per step" if fused else
+                                       f"view-sharded dp{world}, NCCL all-reduce of the flat gradient bucket "
+                                       f"({vp.bucket.nbytes() >> 20} MiB) + radii max per step"),
+                       "wall_s_timed_region": t_wall,
+                       "host_enqueue_ms_per_step_rank0": host_s / a.steps * 1e3, "host_cores": os.cpu_count()},
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu})

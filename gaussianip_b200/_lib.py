@@ -60,6 +60,8 @@ _PROTOS = {
                                 C.c_float, C.c_longlong, _P, _P, _P, _P, _P, _P]),
     "gsb_set_blend_variant": (C.c_int, [C.c_int]),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
+    "gsb_exchange_config": (C.c_int, [C.c_int, C.c_int, C.c_longlong, _P]),
+    "gsb_exchange_gather": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "gsb_mask_index_tmp_bytes": (C.c_size_t, [C.c_longlong]),
     "gsb_mask_to_index": (C.c_int, [C.c_longlong, _P, _P, _P, _P, _P]),
     "gsb_gather_rows": (C.c_int, [C.c_int, _P, _P, _P, C.c_longlong, _P, C.c_longlong, _P]),

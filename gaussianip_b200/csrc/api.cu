@@ -341,6 +341,17 @@ int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix, const
   return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 }
 
+int gsb_exchange_config(int world, int rank, long long rows_per_rank, const void* const* peer_bases) {
+  return set_exchange_peers(world, rank, rows_per_rank, peer_bases);
+}
+
+int gsb_exchange_gather(const float* local_base, float* multicast_base, int n_segments, const long long* offset_floats,
+                        const long long* count_floats, void* stream) {
+  if (n_segments < 0 || (n_segments > 0 && (!offset_floats || !count_floats))) return GSB_E_INVALID;
+  return launch_exchange_gather(local_base, multicast_base, n_segments, offset_floats, count_floats,
+                                (cudaStream_t)stream);
+}
+
 size_t gsb_mask_index_tmp_bytes(long long n) { return mask_index_tmp_bytes(n); }
 
 int gsb_mask_to_index(long long n, const uint8_t* mask, int64_t* index, uint32_t* count, void* tmp, void* stream) {

@@ -153,6 +153,18 @@ int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void
                              long long D_cap, uint64_t* keys_out, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
 int radix_num_passes(int end_bit);
+// fused gradient exchange (preprocess_bwd.cu)
+struct ExchangePeers {
+  int world, rank;
+  long long rows_per_rank;
+  char* base[GSB_MAX_RANKS];        // base address of every rank's copy of the symmetric buffer, as mapped HERE
+};
+struct ExchangeSegments {
+  long long off[GSB_EXCHANGE_MAX_SEGMENTS], count[GSB_EXCHANGE_MAX_SEGMENTS];
+};
+int set_exchange_peers(int world, int rank, long long rows_per_rank, const void* const* bases);
+int launch_exchange_gather(const float* local, float* mc, int n_seg, const long long* off, const long long* count,
+                           cudaStream_t st);
 // densify/prune data movement (compact.cu)
 size_t mask_index_tmp_bytes(long long n);
 int launch_mask_to_index(long long n, const uint8_t* mask, int64_t* index, uint32_t* count, void* tmp, cudaStream_t st);

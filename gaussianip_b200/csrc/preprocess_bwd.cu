@@ -16,6 +16,54 @@ namespace {
 
 __device__ __forceinline__ void put(float* p, float v, int acc) { *p = acc ? (*p + v) : v; }
 
+// ---- accumulate mode 2: the outputs are NVLS MULTICAST addresses of zero-initialised symmetric buffers
+// mapped on every GPU of the step; a multimem.red adds the value into the copy of EVERY rank inside the
+// NVSwitch, so when all ranks' kernels have finished each copy holds the sum over ranks — the gradient
+// all-reduce happens in this kernel's epilogue and overlaps its compute (fused exchange).
+//
+// ---- accumulate mode 3 (scales with the number of ranks): rows are OWNED by ranks in contiguous blocks; the
+// epilogue adds each row with a plain red.global into the OWNER's copy only (peer memory over NVLink, every
+// GPU receives (N-1)/N of one gradient instead of N gradients), and a small second kernel lets every owner
+// multicast its reduced block to all copies (gsb_exchange_gather).
+template <bool MULTIMEM>
+__device__ __forceinline__ void mc_red(float* p, float v) {
+  if (MULTIMEM) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+  else asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+template <bool MULTIMEM>
+__device__ __forceinline__ void mc_red4(float* p, const float4 v) {
+  if (MULTIMEM)
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  else
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+// One warp's rows of a [P, W] tensor are 32*W contiguous floats starting 16 B aligned (first row of a warp is
+// a multiple of 32): stage them through shared memory and emit full 16 B reds instead of W strided 4 B ones.
+template <int W, bool MULTIMEM>
+__device__ __forceinline__ void mc_rows(float* __restrict__ out, float* __restrict__ stage, int first, int n_valid,
+                                        int lane, const float (&v)[W]) {
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < W; ++k) stage[lane * W + k] = v[k];
+  __syncwarp();
+  const int floats = n_valid * W;
+  float* base = out + (size_t)first * W;
+#pragma unroll
+  for (int q = lane; q < (32 * W) / 4; q += 32) {
+    if (4 * q + 3 < floats) {
+      const float4 t = reinterpret_cast<const float4*>(stage)[q];
+      if (t.x != 0.f || t.y != 0.f || t.z != 0.f || t.w != 0.f) mc_red4<MULTIMEM>(base + 4 * q, t);
+    } else {
+      for (int e = 4 * q; e < floats; ++e)
+        if (stage[e] != 0.f) mc_red<MULTIMEM>(base + e, stage[e]);
+    }
+  }
+}
+
 template <int DEG>
 struct Accum {            // per-Gaussian gradient sums over the views of one launch (registers)
   float dp[3], d2[2], dop, dsc[3], dq[4], dcov[6], dcol[3];
@@ -249,15 +297,17 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
   }
 }
 
-template <int DEG>
+template <int DEG, int MODE>     // MODE 0: store / accumulate locally, 2: multicast red into all copies, 3: red into the owner's copy
 __global__ void __launch_bounds__(256, 2)
 preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rots,
                       const float* __restrict__ shs, const float* __restrict__ cov3Dp,
                       float* __restrict__ dmeans3D, float* __restrict__ dmeans2D, float* __restrict__ dshs,
                       float* __restrict__ dcolors, float* __restrict__ dopac, float* __restrict__ dscales,
-                      float* __restrict__ drots, float* __restrict__ dcov3D, int acc) {
+                      float* __restrict__ drots, float* __restrict__ dcov3D, int acc, const ExchangePeers X) {
   constexpr int NC3 = 3 * (DEG + 1) * (DEG + 1);
+  constexpr bool MC = MODE != 0;
+  constexpr bool MM = MODE == 2;
   __shared__ float sV[GSB_MAX_VIEWS][16], sM[GSB_MAX_VIEWS][16], sCam[GSB_MAX_VIEWS][4];
   for (int t = threadIdx.x; t < B.V * 16; t += blockDim.x) {
     sV[t >> 4][t & 15] = B.a[t >> 4].v.view[t & 15];
@@ -270,25 +320,81 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   // reading one's own row touches every fetched sector completely (re-reads across views hit L1)
   const float* my_sh = shs ? shs + (size_t)i * K * 3 : nullptr;
 
-  if (i < P) {
-    Accum<DEG> A;
+  Accum<DEG> A;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { A.dp[k] = 0.f; A.dsc[k] = 0.f; A.dcol[k] = 0.f; }
-    A.d2[0] = A.d2[1] = 0.f; A.dop = 0.f;
+  for (int k = 0; k < 3; ++k) { A.dp[k] = 0.f; A.dsc[k] = 0.f; A.dcol[k] = 0.f; }
+  A.d2[0] = A.d2[1] = 0.f; A.dop = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) A.dq[k] = 0.f;
+  for (int k = 0; k < 4; ++k) A.dq[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) A.dcov[k] = 0.f;
+  for (int k = 0; k < 6; ++k) A.dcov[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NC3; ++k) A.dsh[k] = 0.f;
+  for (int k = 0; k < NC3; ++k) A.dsh[k] = 0.f;
 
+  if (i < P) {
     for (int vi = 0; vi < B.V; ++vi) {
       const BwdView& bv = B.a[vi];
       if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
       view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], means3D, scales, rots, my_sh, cov3Dp, bv.geom, bv.clamped,
                         bv.ggrad, dcolors != nullptr, A);
     }
+  }
 
+  if (MC) {
+    // every lane takes part (shared-memory staging is warp-wide); rows past P carry zeros and are cut off
+    __shared__ float s_stage[8][32 * 6];
+    const int lane = threadIdx.x & 31;
+    float* stage = s_stage[threadIdx.x >> 5];
+    const int first = i - lane;
+    const int n_valid = min(32, P - first);
+    if (n_valid <= 0) return;               // warp-uniform
+    if (MODE == 3) {
+      // this warp's 32 rows belong to one owner (blocks are multiples of 32 rows): retarget every output
+      // from the local copy to the same offset inside the owner's copy
+      int owner = (int)(first / X.rows_per_rank);
+      owner = owner < X.world ? owner : X.world - 1;
+      const ptrdiff_t shift = X.base[owner] - X.base[X.rank];
+      auto to_owner = [&](float* p) { return p ? reinterpret_cast<float*>(reinterpret_cast<char*>(p) + shift) : p; };
+      dmeans3D = to_owner(dmeans3D); dmeans2D = to_owner(dmeans2D); dopac = to_owner(dopac);
+      dcolors = to_owner(dcolors); dcov3D = to_owner(dcov3D); dscales = to_owner(dscales);
+      drots = to_owner(drots); dshs = to_owner(dshs);
+    }
+    mc_rows<3, MM>(dmeans3D, stage, first, n_valid, lane, A.dp);
+    { const float t[3] = {A.d2[0], A.d2[1], 0.f}; mc_rows<3, MM>(dmeans2D, stage, first, n_valid, lane, t); }
+    { const float t[1] = {A.dop}; mc_rows<1, MM>(dopac, stage, first, n_valid, lane, t); }
+    if (dcolors) mc_rows<3, MM>(dcolors, stage, first, n_valid, lane, A.dcol);
+    if (cov3Dp) {
+      mc_rows<6, MM>(dcov3D, stage, first, n_valid, lane, A.dcov);
+    } else {
+      mc_rows<3, MM>(dscales, stage, first, n_valid, lane, A.dsc);
+      if (i < P && (A.dq[0] != 0.f || A.dq[1] != 0.f || A.dq[2] != 0.f || A.dq[3] != 0.f))
+        mc_red4<MM>(drots + 4 * (size_t)i, make_float4(A.dq[0], A.dq[1], A.dq[2], A.dq[3]));
+    }
+    if (dshs) {
+      if (NC3 == 3 && K == 1) {
+        const float t[3] = {A.dsh[0], A.dsh[1], A.dsh[2]};
+        mc_rows<3, MM>(dshs, stage, first, n_valid, lane, t);
+      } else if (i < P) {
+        float* dsh = dshs + (size_t)i * K * 3;
+        if (((K * 3) & 3) == 0) {
+#pragma unroll
+          for (int k = 0; k + 3 < NC3; k += 4)
+            if (A.dsh[k] != 0.f || A.dsh[k + 1] != 0.f || A.dsh[k + 2] != 0.f || A.dsh[k + 3] != 0.f)
+              mc_red4<MM>(dsh + k, make_float4(A.dsh[k], A.dsh[k + 1], A.dsh[k + 2], A.dsh[k + 3]));
+#pragma unroll
+          for (int k = NC3 & ~3; k < NC3; ++k)
+            if (A.dsh[k] != 0.f) mc_red<MM>(dsh + k, A.dsh[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < NC3; ++k)
+            if (A.dsh[k] != 0.f) mc_red<MM>(dsh + k, A.dsh[k]);
+        }
+      }
+    }
+    return;
+  }
+
+  if (i < P) {
     put(dmeans3D + 3 * i, A.dp[0], acc); put(dmeans3D + 3 * i + 1, A.dp[1], acc); put(dmeans3D + 3 * i + 2, A.dp[2], acc);
     put(dmeans2D + 3 * i, A.d2[0], acc); put(dmeans2D + 3 * i + 1, A.d2[1], acc);
     if (!acc) dmeans2D[3 * i + 2] = 0.f;
@@ -331,7 +437,63 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   }
 }
 
+// Second half of the owner-push exchange: copy `count` floats at `off` of the local copy to the same offset of
+// EVERY copy through the multicast mapping (16 B stores; offsets and counts are multiples of 4 floats except
+// possibly the last segment's tail, which goes out as scalars).
+__global__ void __launch_bounds__(256) exchange_gather_kernel(const float* __restrict__ local, float* __restrict__ mc,
+                                                              ExchangeSegments S) {
+  const int seg = blockIdx.y;
+  const long long off = S.off[seg], n = S.count[seg];
+  const float4* src = reinterpret_cast<const float4*>(local + off);
+  float* dst = mc + off;
+  const long long n4 = n >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[q];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long e = (n4 << 2) + threadIdx.x;
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + e), "f"(local[off + e]) : "memory");
+  }
+}
+
 }  // namespace
+
+static ExchangePeers g_peers = {};
+
+int set_exchange_peers(int world, int rank, long long rows_per_rank, const void* const* bases) {
+  if (world < 1 || world > GSB_MAX_RANKS || rank < 0 || rank >= world || rows_per_rank <= 0 || (rows_per_rank & 31) || !bases)
+    return GSB_E_INVALID;
+  ExchangePeers x = {};
+  x.world = world; x.rank = rank; x.rows_per_rank = rows_per_rank;
+  for (int r = 0; r < world; ++r) {
+    if (!bases[r]) return GSB_E_INVALID;
+    x.base[r] = static_cast<char*>(const_cast<void*>(bases[r]));
+  }
+  g_peers = x;
+  return GSB_OK;
+}
+
+int launch_exchange_gather(const float* local, float* mc, int n_seg, const long long* off, const long long* count,
+                           cudaStream_t st) {
+  if (n_seg <= 0) return GSB_OK;
+  if (n_seg > GSB_EXCHANGE_MAX_SEGMENTS || !local || !mc) return GSB_E_INVALID;
+  ExchangeSegments S = {};
+  long long most = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (off[i] < 0 || count[i] < 0 || (off[i] & 3)) return GSB_E_INVALID;
+    S.off[i] = off[i]; S.count[i] = count[i];
+    most = count[i] > most ? count[i] : most;
+  }
+  if (most == 0) return GSB_OK;
+  long long blocks = (most / 4 + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 4 ? 148 * 4 : blocks);
+  exchange_gather_kernel<<<dim3((unsigned)blocks, (unsigned)n_seg), 256, 0, st>>>(local, mc, S);
+  GSB_POST_LAUNCH(false, st, "exchange_gather_kernel");
+  return GSB_OK;
+}
 
 int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D, const float* scales,
                           const float* rots, const float* shs, const float* colors, const float* cov3D,
@@ -340,6 +502,7 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
                           cudaStream_t st) {
   if (P == 0) return GSB_OK;
   if (B.V < 1 || B.V > GSB_MAX_VIEWS) return GSB_E_INVALID;
+  if (accumulate == 3 && g_peers.world < 1) return GSB_E_INVALID;     // gsb_exchange_config was not called
   const int deg = B.a[0].v.sh_degree;
   for (int v = 1; v < B.V; ++v)
     if (B.a[v].v.sh_degree != deg) return GSB_E_INVALID;   // one degree per launch
@@ -354,14 +517,26 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
       int dev = 0;                                                                                              \
       GSB_CUDA(cudaGetDevice(&dev));                                                                            \
       if (!configured[dev & 63]) {                                                                              \
-        GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       64 * 1024));                                                              \
         configured[dev & 63] = true;                                                                            \
       }                                                                                                         \
     }                                                                                                           \
-    preprocess_bwd_kernel<D><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D, dmeans3D,     \
-                                                      dmeans2D, shs ? dshs : nullptr, colors ? dcolors : nullptr, \
-                                                      dopac, dscales, drots, dcov3D, accumulate);                \
+    if (accumulate == 2)                                                                                        \
+      preprocess_bwd_kernel<D, 2><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
+                                                           dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
+                                                           colors ? dcolors : nullptr, dopac, dscales,          \
+                                                           drots, dcov3D, accumulate, g_peers);                 \
+    else if (accumulate == 3)                                                                                   \
+      preprocess_bwd_kernel<D, 3><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
+                                                           dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
+                                                           colors ? dcolors : nullptr, dopac, dscales,          \
+                                                           drots, dcov3D, accumulate, g_peers);                 \
+    else                                                                                                        \
+      preprocess_bwd_kernel<D, 0><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
+                                                           dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
+                                                           colors ? dcolors : nullptr, dopac, dscales,          \
+                                                           drots, dcov3D, accumulate, g_peers);                 \
   } while (0)
   switch (shs ? deg : 0) {
     case 0: GSB_LAUNCH_BWD(0); break;

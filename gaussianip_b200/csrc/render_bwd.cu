@@ -10,11 +10,17 @@
 //    13-shuffle multi-value butterfly and leave the SM as ONE red.global per component per
 //    (warp, Gaussian) — 10 lanes hitting one 48 B GGrad record — instead of ~10 atomicAdd
 //    per (pixel, Gaussian).
+#include <cstdio>
 #include "gsb_common.cuh"
 
 namespace gsb {
 
 namespace {
+
+#ifdef GSB_BWD_STATS
+// measurement build only (GSB_NVCC_EXTRA=-DGSB_BWD_STATS): where do the warp-hits go?
+__device__ unsigned long long g_bwd_stats[12];
+#endif
 
 constexpr int WARPS = 8;
 #ifndef GSB_BWD_STAGES
@@ -136,6 +142,9 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_gid(c));
   uint32_t gid_next = fetch_gid(STAGES - 1);
 
+#ifdef GSB_BWD_STATS
+  unsigned long long st_cand = 0, st_rect = 0, st_any = 0, st_lanes = 0, st_hist[5] = {0, 0, 0, 0, 0};
+#endif
   for (int c = 0; c < chunks; ++c) {
     issue(c + STAGES - 1, gid_next);
     gid_next = fetch_gid(c + STAGES);
@@ -160,6 +169,10 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       hit = (fabsf(a.x - cxw) <= a.z + hwx) && (fabsf(a.y - cyw) <= a.w + hwy);
     }
     uint32_t mask = __ballot_sync(0xffffffffu, hit);
+#ifdef GSB_BWD_STATS
+    st_cand += __popc(__ballot_sync(0xffffffffu, e < n));
+    st_rect += __popc(mask);
+#endif
     // Hits are taken BH at a time (back to front): their geometry/alpha are independent and the
     // 13-shuffle reductions can interleave.
     while (mask) {
@@ -223,6 +236,12 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       //  521 -> 560 us at FRINGE=3, 569 us at FRINGE=1; the butterfly is kept for every hit)
 #pragma unroll
       for (int i = 0; i < BH; ++i) {
+#ifdef GSB_BWD_STATS
+        {
+          const int nv = __popc(__ballot_sync(0xffffffffu, valid[i]));
+          if (nv) { st_any++; st_lanes += nv; st_hist[nv <= 2 ? 0 : nv <= 4 ? 1 : nv <= 8 ? 2 : nv <= 16 ? 3 : 4]++; }
+        }
+#endif
         if (!__any_sync(0xffffffffu, valid[i])) continue;
         const float tot = butterfly12(g[i], lane);
         if (writer && tot != 0.0f)
@@ -232,6 +251,14 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
     __syncwarp();
   }
   cp_async_wait<0>();
+#ifdef GSB_BWD_STATS
+  if (lane == 0) {
+    atomicAdd(&g_bwd_stats[0], (unsigned long long)chunks);
+    atomicAdd(&g_bwd_stats[1], st_cand); atomicAdd(&g_bwd_stats[2], st_rect);
+    atomicAdd(&g_bwd_stats[3], st_any); atomicAdd(&g_bwd_stats[4], st_lanes);
+    for (int i = 0; i < 5; ++i) atomicAdd(&g_bwd_stats[5 + i], st_hist[i]);
+  }
+#endif
 }
 
 }  // namespace
@@ -258,6 +285,16 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
   render_bwd_kernel<<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
                                               dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
   GSB_POST_LAUNCH(debug, st, "render_bwd_kernel");
+#ifdef GSB_BWD_STATS
+  {
+    unsigned long long h[12];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_bwd_stats, sizeof(h));
+    fprintf(stderr, "[bwd stats, cumulative] warp-chunks %llu  candidates %llu  rect-hits %llu  hits-with-valid-lane %llu  "
+            "valid lanes %llu  hist(1-2,3-4,5-8,9-16,17-32) %llu %llu %llu %llu %llu\n", h[0], h[1], h[2], h[3], h[4],
+            h[5], h[6], h[7], h[8], h[9]);
+  }
+#endif
   return GSB_OK;
 }
 

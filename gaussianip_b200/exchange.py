@@ -1,0 +1,160 @@
+"""Gradient exchange fused into the backward kernel (NVLink 5 / NVSwitch).
+
+With views sharded over the GPUs of one box, the only exchange of a step is the SUM over ranks of the
+rasterizer's input gradients.  Instead of letting the per-Gaussian backward kernel write local
+gradients and calling NCCL afterwards, the kernel's epilogue issues ``multimem.red.add`` to the NVLS
+MULTICAST address of a symmetric buffer that is mapped on every GPU: the NVSwitch adds each
+contribution into every rank's copy while the kernel is still computing other Gaussians, so when all
+ranks' kernels have finished every copy already holds the reduced gradient (csrc/preprocess_bwd.cu,
+accumulate mode 2).  Zero-valued rows (Gaussians no local view sees) are not sent at all.
+
+The sum is taken over the gradients with respect to the rasterizer's INPUTS (activated scales,
+opacities, normalised rotations ...).  The activation backward that follows is linear in the incoming
+gradient and identical on all ranks (parameters are replicated), so applying it to the reduced
+gradient yields exactly the reduced leaf gradients — no further exchange is needed.
+
+Two algorithms (csrc/preprocess_bwd.cu, `accumulate` 2 and 3):
+  "push_all"    the epilogue multicasts every row into all copies.  One phase, but every GPU receives N
+                gradients, so it only pays for 2 ranks (measured: +3.5 % views/s at N=2, -3.5 % at N=8).
+  "owner_push"  rows are owned by ranks in contiguous blocks; the epilogue adds each row into the OWNER's
+                copy (plain red.global to peer memory), then every owner multicasts its reduced block to all
+                copies with a small second kernel.  Every GPU receives ~2 gradients whatever N is.
+Protocol per backward (all on the calling stream, no host synchronisation):
+  zero own copy -> barrier(all ranks zeroed) -> [blend backward on side streams] -> fused kernel ->
+  barrier(all ranks' kernels done) [-> gather kernel -> barrier] -> consumers read the local copy.
+
+Buffers come from torch.distributed._symmetric_memory (plumbing: allocation, handle exchange, signal-pad
+barriers); the reduction itself is our kernel.  Requires NVLS multicast support; raises otherwise.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+_FIELDS = (("means3D", 3), ("means2D", 3), ("opacities", 1), ("shs", None), ("colors", 3), ("scales", 3),
+           ("rotations", 4), ("cov3D", 6))
+
+
+class GradExchange:
+    def __init__(self, group=None, clone_outputs: bool = True, algorithm: str = "auto"):
+        """clone_outputs=False hands the backward's consumers views of the symmetric buffer itself (valid until
+        the next backward zeroes it).  Safe when every leaf already has a preallocated ``.grad`` that autograd
+        accumulates INTO (ViewParallel's bucket), because then nothing keeps a reference to the views."""
+        self.clone_outputs = clone_outputs
+        self.algorithm = algorithm
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("GradExchange needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.algorithm == "auto":
+            self.algorithm = "push_all" if self.world <= 2 else "owner_push"
+        if self.algorithm not in ("push_all", "owner_push"):
+            raise ValueError("algorithm must be 'auto', 'push_all' or 'owner_push'")
+        self.mode = 2 if self.algorithm == "push_all" else 3      # `accumulate` value of gsb_preprocess_bwd_views
+        self.key = None
+        self.buf = None
+        self.hdl = None
+        self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        self.steps = 0
+
+    @staticmethod
+    def available(device: torch.device, group=None) -> bool:
+        """COLLECTIVE probe: can every rank of the group map a symmetric buffer with NVLS multicast?  All ranks
+        get the same answer (the local results are combined with a MIN all-reduce)."""
+        ok = 0
+        if torch.cuda.is_available() and dist.is_available() and dist.is_initialized():
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                t = symm_mem.empty(1024, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+                ok = int(bool(getattr(hdl, "has_multicast_support", False)) and bool(hdl.multicast_ptr))
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return bool(flag.item())
+
+    def ensure(self, P: int, K: int, present: Dict[str, bool], device: torch.device) -> None:
+        """(Re)allocate when the shapes change.  COLLECTIVE: every rank must call it with the same shapes."""
+        key = (P, K, tuple(sorted(k for k, v in present.items() if v)), device.index)
+        if key == self.key:
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        off, layout = 0, {}
+        for name, w in _FIELDS:
+            if not present.get(name, False):
+                continue
+            shape = (P, K, 3) if name == "shs" else (P, w)
+            n = 1
+            for d in shape:
+                n *= d
+            layout[name] = (off, shape)
+            off += (n + 63) // 64 * 64            # 256 B alignment of every field
+        self.buf = symm_mem.empty(max(off, 64), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        if not getattr(self.hdl, "has_multicast_support", False) or not self.hdl.multicast_ptr:
+            raise RuntimeError("NVLS multicast is not available on this system; use the NCCL exchange")
+        self.offsets, self.key = layout, key
+        # ownership blocks (owner_push): contiguous row ranges, multiples of 32 rows so a warp has one owner
+        rpr = (-(-P // self.world) + 31) // 32 * 32
+        self.rows_per_rank = max(rpr, 32)
+        r0 = min(self.rank * self.rows_per_rank, P)
+        r1 = P if self.rank == self.world - 1 else min(r0 + self.rows_per_rank, P)
+        self.segments = []
+        for name, (foff, shape) in layout.items():
+            w = 1
+            for d in shape[1:]:
+                w *= d
+            if r1 > r0 and w > 0:
+                self.segments.append((foff + r0 * w, (r1 - r0) * w))
+        if self.mode == 3:
+            import ctypes as C
+            from . import _lib
+            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            arr = (C.c_void_p * self.world)(*ptrs)
+            _lib.check(_lib.load().gsb_exchange_config(self.world, self.rank, self.rows_per_rank, arr),
+                       "gsb_exchange_config")
+
+    def begin(self) -> None:
+        """Zero the local copy and make sure every rank has done so before any contribution can land."""
+        self.buf.zero_()
+        self.hdl.barrier(channel=0)
+
+    def end(self) -> None:
+        """All ranks' kernels (and therefore all their reds) are complete; owner_push then redistributes."""
+        self.hdl.barrier(channel=1)
+        if self.mode == 3 and self.segments:
+            import ctypes as C
+            from . import _lib
+            n = len(self.segments)
+            off = (C.c_longlong * n)(*[o for o, _ in self.segments])
+            cnt = (C.c_longlong * n)(*[c for _, c in self.segments])
+            dev = self.buf.device
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().gsb_exchange_gather(self.buf.data_ptr(), int(self.hdl.multicast_ptr), n, off, cnt,
+                                                           torch.cuda.current_stream(dev).cuda_stream),
+                           "gsb_exchange_gather")
+            self.hdl.barrier(channel=2)
+        self.steps += 1
+
+    def output_ptr(self, name: str) -> Optional[int]:
+        """What the kernel is given for this field: the multicast address (push_all) or the local copy (owner_push)."""
+        if name not in self.offsets:
+            return None
+        base = int(self.hdl.multicast_ptr) if self.mode == 2 else self.buf.data_ptr()
+        return base + 4 * self.offsets[name][0]
+
+    def local(self, name: str) -> Optional[torch.Tensor]:
+        if name not in self.offsets:
+            return None
+        off, shape = self.offsets[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return self.buf[off:off + n].view(shape)
+
+    def nbytes(self) -> int:
+        return 0 if self.buf is None else self.buf.numel() * 4

@@ -389,7 +389,7 @@ def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rota
 
 
 def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
-                    g_color, g_depth, g_alpha):
+                    g_color, g_depth, g_alpha, exchange=None):
     """Backward of V views: the blend backward of view v runs on side stream v (they overlap);
     the per-Gaussian stage runs view after view on the calling stream because it accumulates
     (beta = 1) into one set of gradient tensors."""
@@ -400,11 +400,23 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
     with torch.cuda.device(device):
         main = torch.cuda.current_stream(device)
         e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=device)
-        out = {"means3D": e(P, 3), "means2D": e(P, 3), "opacities": e(P, 1),
-               "shs": e(P, K, 3) if shs is not None else None, "colors": e(P, 3) if colors is not None else None,
-               "scales": e(P, 3) if scales is not None else None,
-               "rotations": e(P, 4) if rotations is not None else None,
-               "cov3D": e(P, 6) if cov3D is not None else None}
+        if exchange is not None:
+            # fused exchange (gaussianip_b200/exchange.py): the per-Gaussian kernel adds into NVLS multicast
+            # addresses; `out` are this rank's views of the symmetric buffer, `optr` what the kernel is given
+            exchange.ensure(P, K, {"means3D": True, "means2D": True, "opacities": True, "shs": shs is not None,
+                                   "colors": colors is not None, "scales": scales is not None,
+                                   "rotations": rotations is not None, "cov3D": cov3D is not None}, device)
+            exchange.begin()                 # zero + barrier, overlaps the blend backward on the side streams
+            out = {k: exchange.local(k) for k in ("means3D", "means2D", "opacities", "shs", "colors", "scales",
+                                                  "rotations", "cov3D")}
+            optr = {k: exchange.output_ptr(k) for k in out}
+        else:
+            out = {"means3D": e(P, 3), "means2D": e(P, 3), "opacities": e(P, 1),
+                   "shs": e(P, K, 3) if shs is not None else None, "colors": e(P, 3) if colors is not None else None,
+                   "scales": e(P, 3) if scales is not None else None,
+                   "rotations": e(P, 4) if rotations is not None else None,
+                   "cov3D": e(P, 6) if cov3D is not None else None}
+            optr = {k: _ptr(t) for k, t in out.items()}
 
         def grad_in(g, shape):
             if g is None:
@@ -444,11 +456,16 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
             dcp = (C.c_longlong * n)(*[svs[v0 + j].d_cap for j in range(n)])
             rc = lib.gsb_preprocess_bwd_views(n, sp, P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
                                               _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), rp, svp, scp,
-                                              dcp, _ptr(out["means3D"]), _ptr(out["means2D"]), _ptr(out["shs"]),
-                                              _ptr(out["colors"]), _ptr(out["opacities"]), _ptr(out["scales"]),
-                                              _ptr(out["rotations"]), _ptr(out["cov3D"]), int(v0 > 0),
+                                              dcp, optr["means3D"], optr["means2D"], optr["shs"],
+                                              optr["colors"], optr["opacities"], optr["scales"],
+                                              optr["rotations"], optr["cov3D"],
+                                              exchange.mode if exchange is not None else int(v0 > 0),
                                               main.cuda_stream)
             _lib.check(rc, "gsb_preprocess_bwd_views")
+        if exchange is not None:
+            exchange.end()                   # every rank's reds have landed: the local copy is the global sum
+            if exchange.clone_outputs:
+                out = {k: (None if t is None else t.clone()) for k, t in out.items()}
         # the side streams' scratch blocks are read by the calling stream above; they are persistent
         # per-(device, stream) workspaces, so no allocator hand-over is involved
         for st in streams[:V]:
@@ -531,9 +548,10 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                settings_list):
+                settings_list, exchange=None):
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = _prepare_inputs(
             means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        ctx.exchange = exchange
         V = len(settings_list)
         if V == 0:
             raise ValueError("no views")
@@ -584,14 +602,14 @@ class _RasterizeViews(torch.autograd.Function):
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         means3D, sh, colors, opacities, scales, rotations, cov3D, radii = ctx.saved_tensors
         has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
-        if ctx.multistream:
+        if ctx.multistream or ctx.exchange is not None:
             out = _backward_views(ctx.settings_list, ctx.svs, means3D, sh if has_sh else None,
                                   colors if has_col else None, opacities, scales if has_sc else None,
                                   rotations if has_rot else None, cov3D if has_cov else None, radii,
-                                  grad_color, grad_depth, grad_alpha)
+                                  grad_color, grad_depth, grad_alpha, exchange=ctx.exchange)
             ctx.svs = None
             return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
-                    out["rotations"], out["cov3D"], None)
+                    out["rotations"], out["cov3D"], None, None)
         out = None
         for v, (rs, sv) in enumerate(zip(ctx.settings_list, ctx.svs)):
             out = _backward_impl(rs, sv, means3D, sh if has_sh else None, colors if has_col else None, opacities,
@@ -602,20 +620,22 @@ class _RasterizeViews(torch.autograd.Function):
                                  None if grad_alpha is None else grad_alpha[v], out=out, accumulate=v > 0)
         ctx.svs = None
         return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
-                out["rotations"], out["cov3D"], None)
+                out["rotations"], out["cov3D"], None, None)
 
 
 def rasterize_views(settings_list, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
-                    rotations=None, cov3D_precomp=None):
+                    rotations=None, cov3D_precomp=None, exchange=None):
     """Batched form of GaussianRasterizer(...)(...): returns stacked (color [V,3,H,W], radii [V,P],
-    depth [V,1,H,W], alpha [V,1,H,W]); means2D.grad receives the SUM over views."""
+    depth [V,1,H,W], alpha [V,1,H,W]); means2D.grad receives the SUM over views.  With
+    ``exchange`` (gaussianip_b200.exchange.GradExchange) the input gradients returned by the backward
+    are already summed over the ranks of the exchange's group (reduction fused into the kernel)."""
     if (shs is None) == (colors_precomp is None):
         raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                 cov3D_precomp, tuple(settings_list))
+                                 cov3D_precomp, tuple(settings_list), exchange)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

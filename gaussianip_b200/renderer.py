@@ -91,7 +91,7 @@ render_with_smaller_scale = render
 
 
 def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
-                 screenspace_points=None):
+                 screenspace_points=None, exchange=None):
     """All views of one optimisation step in ONE call (additive API; the reference loops
     ``render`` over the views in Python, threestudio/systems/GaussianIP.py:154-159, 305-307).
 
@@ -100,7 +100,8 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
     of once per view, there is one autograd node, and ``viewspace_points.grad`` receives the sum
     over views directly.  Returns the ``render`` dictionary with a leading view axis:
     render [V,3,H,W], depth_3dgs / alpha_3dgs [V,1,H,W], radii_per_view [V,P], radii = max over
-    views [P], visibility_filter = radii > 0."""
+    views [P], visibility_filter = radii > 0.  ``exchange``: see rasterize_views (multi-GPU, gradients reduced
+    over ranks inside the backward kernel)."""
     xyz = _get(pc, "get_xyz")
     if screenspace_points is None:
         screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
@@ -126,7 +127,7 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
     image, radii_v, depth, alpha = rasterize_views(
         settings, means3D=xyz.float(), means2D=screenspace_points.float(), shs=f(shs),
         colors_precomp=colors_precomp, opacities=_get(pc, "get_opacity").float(), scales=f(scales),
-        rotations=f(rotations), cov3D_precomp=cov3D_precomp)
+        rotations=f(rotations), cov3D_precomp=cov3D_precomp, exchange=exchange)
     radii = radii_v.max(dim=0).values
     return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii, "radii_per_view": radii_v, "depth_3dgs": depth, "alpha_3dgs": alpha}

@@ -211,6 +211,26 @@ size_t gsb_knn_scratch_bytes(long long P);
 int gsb_knn_dist2(long long P, const float* points, float* mean_dist2, void* scratch,
                   size_t scratch_bytes, void* stream);
 
+/* gradient exchange fused into gsb_preprocess_bwd_views (multi-GPU, one process per GPU).
+ * The gradient outputs live in a SYMMETRIC buffer: same layout on every rank, every rank's copy mapped into
+ * every process (peer memory over NVLink) plus one NVLS multicast mapping of all copies.  `accumulate` selects:
+ *   2  outputs are MULTICAST addresses: the kernel's epilogue multimem.red-adds every row into all copies
+ *      (one kernel, no second phase; every GPU receives N gradients -> best for 2 ranks);
+ *   3  outputs are addresses in the LOCAL copy: rows are owned by ranks in blocks of rows_per_rank; the epilogue
+ *      red-adds each row into the owner's copy only, then gsb_exchange_gather lets every owner multicast its
+ *      reduced block to all copies (every GPU receives ~2 gradients for any N).
+ * Copies must be zero (mode 2: everywhere; mode 3: at least the owned block) before any rank's kernel starts and
+ * ranks must meet at a barrier between the phases — the caller's job (gaussianip_b200/exchange.py).
+ * gsb_exchange_config: process-wide table for mode 3; peer_bases[r] = base of rank r's copy as mapped in THIS
+ * process (peer_bases[rank] = the local copy); rows_per_rank must be a multiple of 32. */
+#define GSB_MAX_RANKS 16
+#define GSB_EXCHANGE_MAX_SEGMENTS 8
+int gsb_exchange_config(int world, int rank, long long rows_per_rank, const void* const* peer_bases);
+/* For each segment s < n_segments: floats [offset[s], offset[s] + count[s]) of the local copy are stored to the
+ * same offsets of every copy through multicast_base (offsets multiples of 4 floats). */
+int gsb_exchange_gather(const float* local_base, float* multicast_base, int n_segments,
+                        const long long* offset_floats, const long long* count_floats, void* stream);
+
 /* data movement of densify / clone / split / prune (gaussian_model.py:281-418).
  * gsb_mask_to_index: stable stream compaction — index[0..count) = positions of the non-zero mask bytes in
  *   ascending order (what `tensor[mask]` / torch.nonzero use), count[0] = how many; device-side, asynchronous.

@@ -111,3 +111,22 @@ def test_densification_stats_match_reference_formulas():
     assert torch.equal(vis, f)
     torch.testing.assert_close(acc, exp_acc)
     assert torch.equal(den, exp_den) and torch.equal(mr, exp_mr)
+
+
+def test_balanced_sharding_partitions_and_balances():
+    import random
+    from gaussianip_b200.multiview import shard_views_balanced, view_cost_proxy
+    rnd = random.Random(3)
+    for world, per in ((2, 4), (8, 4), (4, 3), (8, 1)):
+        costs = [view_cost_proxy(rnd.uniform(1.3, 1.7), rnd.uniform(0.7, 1.22)) for _ in range(world * per)]
+        parts = [shard_views_balanced(costs, r, world) for r in range(world)]
+        assert sorted(v for p in parts for v in p) == list(range(world * per))       # a partition
+        assert all(len(p) == per for p in parts)                                      # same number of views each
+        loads = [sum(costs[v] for v in p) for p in parts]
+        naive = [sum(costs[v] for v in range(r, world * per, world)) for r in range(world)]
+        assert max(loads) <= max(naive) + 1e-12
+        if per >= 3:
+            assert max(loads) / (sum(loads) / world) < 1.15
+    assert shard_views_balanced([1.0, 1.0, 1.0], 0, 2) == [0]                         # ties broken by index,
+    assert shard_views_balanced([1.0, 1.0, 1.0], 1, 2) == [1, 2]                      # dealt in snake order
+    assert shard_views_balanced([], 0, 2) == []
