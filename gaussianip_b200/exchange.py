@@ -19,8 +19,8 @@ Two algorithms (csrc/preprocess_bwd.cu, `accumulate` 2 and 3):
   "owner_push"  rows are owned by ranks in contiguous blocks; the epilogue adds each row into the OWNER's
                 copy (plain red.global to peer memory), then every owner multicasts its reduced block to all
                 copies with a small second kernel.  Every GPU receives ~2 gradients whatever N is.
-Protocol per backward (all on the calling stream, no host synchronisation):
-  zero own copy -> barrier(all ranks zeroed) -> [blend backward on side streams] -> fused kernel ->
+Protocol per backward (all on the calling stream, no host synchronisation); the buffer has two halves used in turn:
+  zero the OTHER half (next step's) -> [blend backward on side streams] -> fused kernel into this half ->
   barrier(all ranks' kernels done) [-> gather kernel -> barrier] -> consumers read the local copy.
 
 Buffers come from torch.distributed._symmetric_memory (plumbing: allocation, handle exchange, signal-pad
@@ -93,7 +93,10 @@ class GradExchange:
                 n *= d
             layout[name] = (off, shape)
             off += (n + 63) // 64 * 64            # 256 B alignment of every field
-        self.buf = symm_mem.empty(max(off, 64), dtype=torch.float32, device=device)
+        # two halves used alternately: the half of step k+1 is zeroed during step k and step k's closing barrier
+        # tells every rank so, which saves the "everyone has zeroed" barrier in front of each kernel
+        self.half = max(off, 64)
+        self.buf = symm_mem.empty(2 * self.half, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         if not getattr(self.hdl, "has_multicast_support", False) or not self.hdl.multicast_ptr:
             raise RuntimeError("NVLS multicast is not available on this system; use the NCCL exchange")
@@ -117,11 +120,16 @@ class GradExchange:
             arr = (C.c_void_p * self.world)(*ptrs)
             _lib.check(_lib.load().gsb_exchange_config(self.world, self.rank, self.rows_per_rank, arr),
                        "gsb_exchange_config")
+        self.buf.zero_()
+        self.hdl.barrier(channel=0)          # both halves are zero everywhere before the first kernel
+        self.cur = 0
 
     def begin(self) -> None:
-        """Zero the local copy and make sure every rank has done so before any contribution can land."""
-        self.buf.zero_()
-        self.hdl.barrier(channel=0)
+        """Pick this step's half (already zero on every rank) and zero the other one for the next step; the
+        zeroing is ordered before this step's closing barrier, so nobody can add into it too early."""
+        self.cur = self.steps & 1
+        other = 1 - self.cur
+        self.buf[other * self.half:(other + 1) * self.half].zero_()
 
     def end(self) -> None:
         """All ranks' kernels (and therefore all their reds) are complete; owner_push then redistributes."""
@@ -130,7 +138,7 @@ class GradExchange:
             import ctypes as C
             from . import _lib
             n = len(self.segments)
-            off = (C.c_longlong * n)(*[o for o, _ in self.segments])
+            off = (C.c_longlong * n)(*[o + self.cur * self.half for o, _ in self.segments])
             cnt = (C.c_longlong * n)(*[c for _, c in self.segments])
             dev = self.buf.device
             with torch.cuda.device(dev):
@@ -145,16 +153,17 @@ class GradExchange:
         if name not in self.offsets:
             return None
         base = int(self.hdl.multicast_ptr) if self.mode == 2 else self.buf.data_ptr()
-        return base + 4 * self.offsets[name][0]
+        return base + 4 * (self.offsets[name][0] + self.cur * self.half)
 
     def local(self, name: str) -> Optional[torch.Tensor]:
         if name not in self.offsets:
             return None
         off, shape = self.offsets[name]
+        off += self.cur * self.half
         n = 1
         for d in shape:
             n *= d
         return self.buf[off:off + n].view(shape)
 
     def nbytes(self) -> int:
-        return 0 if self.buf is None else self.buf.numel() * 4
+        return 0 if self.buf is None else self.half * 4
