@@ -13,6 +13,7 @@ ap.add_argument("--views", type=int, default=4)
 ap.add_argument("--sh", type=int, default=0)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--algo", default="auto")
+ap.add_argument("--precomp", action="store_true", help="precomputed colours + 3D covariances (other gradient rows)")
 a = ap.parse_args()
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -34,6 +35,17 @@ class Model:
     get_scaling = property(lambda s: torch.exp(s.p["scaling"]))
     get_rotation = property(lambda s: torch.nn.functional.normalize(s.p["rotation"]))
 
+    def get_covariance(self, scaling_modifier=1.0):
+        """[P,6] upper triangle of R S S^T R^T (gaussian_model.py:24-29), differentiable."""
+        q = self.get_rotation
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3)
+        L = R * (scaling_modifier * self.get_scaling)[:, None, :]
+        S = L @ L.transpose(1, 2)
+        return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=1)
+
 
 n_total = a.views * world
 cams = synthetic.ahds_cameras(n_total, a.res, a.res, seed=1, device=dev)
@@ -47,8 +59,14 @@ def run(fused):
     model = Model(params)
     vp = multiview.ViewParallel(params, a.points, fused_exchange=fused, exchange_algorithm=a.algo)
 
+    class Pipe:
+        compute_cov3D_python = a.precomp
+        convert_SHs_python = False
+
     def render_views_fn(views, vsp, exchange=None):
-        return renderer.render_views([cams[v] for v in views], model, None, bg, screenspace_points=vsp, exchange=exchange)
+        override = torch.sigmoid(params["features_dc"][:, 0, :]) if a.precomp else None
+        return renderer.render_views([cams[v] for v in views], model, Pipe, bg, override_color=override,
+                                     screenspace_points=vsp, exchange=exchange)
 
     def loss_fn(views, out):
         idx = torch.tensor(views, device=dev)

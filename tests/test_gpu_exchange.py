@@ -12,13 +12,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("algo", ["push_all", "owner_push"])
-def test_fused_exchange_equals_nccl_all_reduce(algo):
+@pytest.mark.parametrize("algo,extra", [("push_all", ["--sh", "1"]), ("owner_push", ["--sh", "1"]),
+                                        ("owner_push", ["--precomp"]), ("push_all", ["--precomp", "--points", "50001"])])
+def test_fused_exchange_equals_nccl_all_reduce(algo, extra):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "exchange_check.py"), "--algo", algo,
-           "--points", "60000", "--res", "256", "--views", "2", "--sh", "1", "--steps", "3"]
+           "--points", "60000", "--res", "256", "--views", "2", "--steps", "3"] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
