@@ -55,6 +55,9 @@ def parse():
                     help="N>1: all-reduce the gradient bucket with NCCL, or reduce inside the backward kernel "
                          "over NVLink peer / NVLS multicast memory (gaussianip_b200/exchange.py); auto = fused "
                          "when every rank can map multicast memory, else NCCL")
+    ap.add_argument("--torch-activations", action="store_true",
+                    help="evaluate sigmoid/exp/normalize with torch around the operator (the reference's getters) "
+                         "instead of inside the per-Gaussian kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -232,6 +235,9 @@ def main():
 
         def __init__(self, p):
             self.p = p
+        _opacity = property(lambda s: s.p["opacity"])       # the raw parameters, reference attribute names
+        _scaling = property(lambda s: s.p["scaling"])
+        _rotation = property(lambda s: s.p["rotation"])
         get_xyz = property(lambda s: s.p["xyz"])
         get_features = property(lambda s: torch.cat((s.p["features_dc"], s.p["features_rest"]), dim=1))
         get_opacity = property(lambda s: torch.sigmoid(s.p["opacity"]))
@@ -303,7 +309,7 @@ def main():
         # the single-view operator; activations evaluated once per step, one autograd node)
         def render_views_fn(views, vsp, exchange=None):
             return renderer.render_views([cams[v] for v in views], model, None, bg, screenspace_points=vsp,
-                                         exchange=exchange)
+                                         exchange=exchange, fused_activations=not a.torch_activations)
         return vp.step_batched(a.views, render_views_fn, loss_of, views=range(a.views))
 
     def device_cams(step_idx):
@@ -479,6 +485,8 @@ def main():
             "config": {"workload": workload_name(a), "points": a.points, "resolution": a.res,
                        "views_per_step_per_gpu": a.views, "sh_degree": a.sh_degree, "num_rendered_D": D,
                        "l2": "256 MiB flush write between timed steps (outside the event pairs)",
+                       "activations": "torch getters around the operator" if a.torch_activations else
+                                      "fused into the per-Gaussian kernels (render_views(fused_activations=True))",
                        "view_sharding": "n/a" if world == 1 else a.view_sharding,
                        "parallelism": ("single GPU" if world == 1 else
                                        f"view-sharded dp{world}, gradients reduced INSIDE the backward kernel "

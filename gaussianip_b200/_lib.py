@@ -11,12 +11,15 @@ LIB_PATH = _PKG / "libgsb.so"
 GSB_OK, GSB_E_INVALID, GSB_E_CUDA, GSB_E_CAPACITY, GSB_E_UNSUPPORTED = 0, -1, -2, -3, -4
 BIN_TWO_LEVEL, BIN_FLAT64 = 0, 1
 MAX_VIEWS = 8
+ABI_VERSION = 2
+RAW_OPACITY, RAW_SCALE, RAW_ROTATION = 1, 2, 4
 
 
 class GsbSettings(C.Structure):
     _fields_ = [("image_height", C.c_int32), ("image_width", C.c_int32),
                 ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
                 ("sh_degree", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
+                ("raw_inputs", C.c_int32),
                 ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
                 ("campos", C.c_void_p)]
 
@@ -91,7 +94,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if an include/gsb.h symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.gsb_abi_version() != 1:
+    if lib.gsb_abi_version() != ABI_VERSION:
         raise RuntimeError("libgsb.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -62,7 +62,8 @@ static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static bool settings_ok(const GsbSettings* s) {
   return s && s->image_height > 0 && s->image_width > 0 && s->sh_degree >= 0 && s->sh_degree <= 3 && s->bg &&
          s->viewmatrix && s->projmatrix && s->campos && s->tanfovx > 0.f && s->tanfovy > 0.f &&
-         s->image_width <= 65535 * TILE_X && s->image_height <= 65535 * TILE_Y;
+         s->image_width <= 65535 * TILE_X && s->image_height <= 65535 * TILE_Y &&
+         (s->raw_inputs & ~(GSB_RAW_OPACITY | GSB_RAW_SCALE | GSB_RAW_ROTATION)) == 0;
 }
 
 static int layout(int P, int H, int W, long long D_cap, GsbLayout* L) {

@@ -40,6 +40,7 @@ struct View {           // settings with device pointers, passed by value to ker
   int H, W, gx, gy;     // image size, tile grid
   float tanfovx, tanfovy, focal_x, focal_y, scale_mod;
   int sh_degree;
+  int raw;              // GSB_RAW_* bits
   const float* bg;
   const float* view;
   const float* proj;
@@ -53,9 +54,17 @@ inline View make_view(const GsbSettings* s) {
   v.tanfovx = s->tanfovx; v.tanfovy = s->tanfovy;
   v.focal_x = (float)v.W / (2.0f * s->tanfovx);
   v.focal_y = (float)v.H / (2.0f * s->tanfovy);
-  v.scale_mod = s->scale_modifier; v.sh_degree = s->sh_degree;
+  v.scale_mod = s->scale_modifier; v.sh_degree = s->sh_degree; v.raw = s->raw_inputs;
   v.bg = s->bg; v.view = s->viewmatrix; v.proj = s->projmatrix; v.campos = s->campos;
   return v;
+}
+
+// Activations of the raw model parameters (GSB_RAW_*), written the way torch evaluates them.
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float4 act_normalize(float4 q, float* norm_out = nullptr) {
+  const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);   // F.normalize eps
+  if (norm_out) *norm_out = n;
+  return make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
 }
 
 template <typename T>

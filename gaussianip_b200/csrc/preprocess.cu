@@ -74,9 +74,11 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
       const float* c = cov3Dp + 6 * (size_t)i;
       S00 = c[0]; S01 = c[1]; S02 = c[2]; S11 = c[3]; S12 = c[4]; S22 = c[5];
     } else {
-      const float sx = v.scale_mod * scales[3 * i], sy = v.scale_mod * scales[3 * i + 1],
-                  sz = v.scale_mod * scales[3 * i + 2];
-      const float4 q = reinterpret_cast<const float4*>(rots)[i];
+      float s0 = scales[3 * i], s1 = scales[3 * i + 1], s2 = scales[3 * i + 2];
+      if (v.raw & GSB_RAW_SCALE) { s0 = expf(s0); s1 = expf(s1); s2 = expf(s2); }
+      const float sx = v.scale_mod * s0, sy = v.scale_mod * s1, sz = v.scale_mod * s2;
+      float4 q = reinterpret_cast<const float4*>(rots)[i];
+      if (v.raw & GSB_RAW_ROTATION) q = act_normalize(q);
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       const float m00 = (1.0f - 2.0f * (y * y + z * z)) * sx, m01 = (2.0f * (x * y - r * z)) * sy,
                   m02 = (2.0f * (x * z + r * y)) * sz;
@@ -149,7 +151,7 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
           if (g_ < 0.0f) { cl |= 2; g_ = 0.0f; }
           if (b_ < 0.0f) { cl |= 4; b_ = 0.0f; }
         }
-        const float o = opac[i];
+        const float o = (v.raw & GSB_RAW_OPACITY) ? act_sigmoid(opac[i]) : opac[i];
         // Conservative half-extent (pixels) of the region where alpha = o*exp(power) can
         // reach 1/255: bounding box of {d : 0.5 d^T Q d <= ln(255 o)} is sqrt(2 tau cov_ii).
         // Used only to SKIP work that would be discarded anyway; padded against rounding.

@@ -76,7 +76,7 @@ struct Accum {            // per-Gaussian gradient sums over the views of one la
 template <int DEG>
 __device__ __forceinline__ void
 view_contrib(const View& v, int i, const float* sV, const float* sM, const float* sCam,
-             const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rots,
+             const float* __restrict__ means3D, const float (&sc_act)[3], const float4 q_act,
              const float* sh, const float* __restrict__ cov3Dp, const Geom* __restrict__ geom,
              const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, bool precomp_color,
              Accum<DEG>& A) {
@@ -178,8 +178,8 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
     const float* c = cov3Dp + 6 * (size_t)i;
     S00 = c[0]; S01 = c[1]; S02 = c[2]; S11 = c[3]; S12 = c[4]; S22 = c[5];
   } else {
-    s[0] = v.scale_mod * scales[3 * i]; s[1] = v.scale_mod * scales[3 * i + 1]; s[2] = v.scale_mod * scales[3 * i + 2];
-    const float4 q = reinterpret_cast<const float4*>(rots)[i];
+    s[0] = v.scale_mod * sc_act[0]; s[1] = v.scale_mod * sc_act[1]; s[2] = v.scale_mod * sc_act[2];
+    const float4 q = q_act;
     qr = q.x; qx = q.y; qy = q.z; qz = q.w;
     R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
     R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
@@ -332,11 +332,32 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   for (int k = 0; k < NC3; ++k) A.dsh[k] = 0.f;
 
   if (i < P) {
+    // scale / rotation are loaded (and, for raw model parameters, activated) once for all views
+    const int raw = B.a[0].v.raw;
+    float sc[3] = {0.f, 0.f, 0.f}, qn = 1.f, o_act = 0.f;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!cov3Dp) {
+      sc[0] = scales[3 * i]; sc[1] = scales[3 * i + 1]; sc[2] = scales[3 * i + 2];
+      if (raw & GSB_RAW_SCALE) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
+      q = reinterpret_cast<const float4*>(rots)[i];
+      if (raw & GSB_RAW_ROTATION) q = act_normalize(q, &qn);
+    }
     for (int vi = 0; vi < B.V; ++vi) {
       const BwdView& bv = B.a[vi];
       if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
-      view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], means3D, scales, rots, my_sh, cov3Dp, bv.geom, bv.clamped,
+      view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], means3D, sc, q, my_sh, cov3Dp, bv.geom, bv.clamped,
                         bv.ggrad, dcolors != nullptr, A);
+      o_act = reinterpret_cast<const float4*>(bv.geom + i)[1].w;      // activated opacity, as the forward stored it
+    }
+    // chain rule to the RAW parameters, applied once to the sum over views
+    if (raw & GSB_RAW_OPACITY) A.dop = A.dop * (1.0f - o_act) * o_act;                    // sigmoid'
+    if (!cov3Dp) {
+      if (raw & GSB_RAW_SCALE) { A.dsc[0] *= sc[0]; A.dsc[1] *= sc[1]; A.dsc[2] *= sc[2]; }   // exp'
+      if (raw & GSB_RAW_ROTATION) {                                                       // (I - q q^T) / |raw|
+        const float dot = q.x * A.dq[0] + q.y * A.dq[1] + q.z * A.dq[2] + q.w * A.dq[3];
+        A.dq[0] = (A.dq[0] - q.x * dot) / qn; A.dq[1] = (A.dq[1] - q.y * dot) / qn;
+        A.dq[2] = (A.dq[2] - q.z * dot) / qn; A.dq[3] = (A.dq[3] - q.w * dot) / qn;
+      }
     }
   }
 

@@ -120,7 +120,7 @@ def _small(t: torch.Tensor, n: int, name: str, device) -> torch.Tensor:
     return t
 
 
-def _make_settings(rs: GaussianRasterizationSettings, device):
+def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0):
     bg = _small(rs.bg, 3, "bg", device)
     view = _small(rs.viewmatrix, 16, "viewmatrix", device)
     proj = _small(rs.projmatrix, 16, "projmatrix", device)
@@ -129,7 +129,7 @@ def _make_settings(rs: GaussianRasterizationSettings, device):
         raise ValueError("sh_degree must be in 0..3")
     s = _lib.GsbSettings(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
                          float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)),
-                         int(bool(rs.debug)), bg.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                         int(bool(rs.debug)), int(raw), bg.data_ptr(), view.data_ptr(), proj.data_ptr(),
                          campos.data_ptr())
     return s, (bg, view, proj, campos)      # keep the tensors alive next to the struct
 
@@ -174,7 +174,8 @@ class _ForwardCall:
     the 32-byte counts copy and, if D exceeded the instance capacity, re-enqueues with a larger
     workspace (nothing can have observed the outputs yet)."""
 
-    def __init__(self, rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):
+    def __init__(self, rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0):
+        self.raw = raw
         self.args = (means3D, shs, colors, opacities, scales, rotations, cov3D)
         device = means3D.device
         if device.type != "cuda":
@@ -195,7 +196,7 @@ class _ForwardCall:
             if self.stream is None:
                 self.stream = torch.cuda.current_stream(device)
                 self.ws = _workspace(device)
-                self.s, self.keep = _make_settings(self.rs, device)
+                self.s, self.keep = _make_settings(self.rs, device, self.raw)
                 if self.out is not None:
                     self.color, self.radii, self.depth, self.alpha = self.out   # caller-owned contiguous slices
                 else:
@@ -313,8 +314,8 @@ def _active_speculation():
     return getattr(_tls, "spec", None)
 
 
-def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None):
-    return _ForwardCall(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out).enqueue().finish()
+def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0):
+    return _ForwardCall(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out, raw).enqueue().finish()
 
 
 # Side streams for the batched multi-view entry: the binning stages of a 1-2 M instance view are
@@ -351,14 +352,14 @@ def _streams_for(device: torch.device, n: int):
 
 
 def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
-                   g_color, g_depth, g_alpha, out=None, accumulate=False):
+                   g_color, g_depth, g_alpha, out=None, accumulate=False, raw: int = 0):
     lib = _lib.load()
     device = means3D.device
     P, K, H, W = sv.P, sv.K, sv.H, sv.W
     with torch.cuda.device(device):
         ws = _workspace(device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        s, keep = _make_settings(rs, device)
+        s, keep = _make_settings(rs, device, raw)
         scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
 
         def grad_in(g, shape):
@@ -389,7 +390,7 @@ def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rota
 
 
 def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
-                    g_color, g_depth, g_alpha, exchange=None):
+                    g_color, g_depth, g_alpha, exchange=None, raw: int = 0):
     """Backward of V views: the blend backward of view v runs on side stream v (they overlap);
     the per-Gaussian stage runs view after view on the calling stream because it accumulates
     (beta = 1) into one set of gradient tensors."""
@@ -433,7 +434,7 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 ws = _workspace(device)
-                s, keep = _make_settings(rs, device)
+                s, keep = _make_settings(rs, device, raw)
                 scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
                 rc = lib.gsb_render_bwd(C.byref(s), P, sv.block.data_ptr(), scratch.data_ptr(), sv.d_cap,
                                         g_color[v].data_ptr(), g_depth[v].data_ptr(), g_alpha[v].data_ptr(),
@@ -548,10 +549,14 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                settings_list, exchange=None):
+                settings_list, exchange=None, raw=0):
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = _prepare_inputs(
             means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         ctx.exchange = exchange
+        ctx.raw = raw = int(raw)
+        if cov3Ds_precomp is not None:
+            raw &= ~(_lib.RAW_SCALE | _lib.RAW_ROTATION)
+            ctx.raw = raw
         V = len(settings_list)
         if V == 0:
             raise ValueError("no views")
@@ -576,7 +581,8 @@ class _RasterizeViews(torch.autograd.Function):
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
                     calls.append(_ForwardCall(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
-                                              cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v])).enqueue())
+                                              cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]),
+                                              raw=raw).enqueue())
             for call, st in zip(calls, streams):
                 svs.append(call.finish()[4])
                 join = torch.cuda.Event()
@@ -585,7 +591,7 @@ class _RasterizeViews(torch.autograd.Function):
         else:
             for v, rs in enumerate(settings_list):
                 _, _, _, _, sv = _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
-                                               cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]))
+                                               cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]), raw=raw)
                 svs.append(sv)
         ctx.settings_list, ctx.svs = list(settings_list), svs
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,
@@ -606,10 +612,10 @@ class _RasterizeViews(torch.autograd.Function):
             out = _backward_views(ctx.settings_list, ctx.svs, means3D, sh if has_sh else None,
                                   colors if has_col else None, opacities, scales if has_sc else None,
                                   rotations if has_rot else None, cov3D if has_cov else None, radii,
-                                  grad_color, grad_depth, grad_alpha, exchange=ctx.exchange)
+                                  grad_color, grad_depth, grad_alpha, exchange=ctx.exchange, raw=ctx.raw)
             ctx.svs = None
             return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
-                    out["rotations"], out["cov3D"], None, None)
+                    out["rotations"], out["cov3D"], None, None, None)
         out = None
         for v, (rs, sv) in enumerate(zip(ctx.settings_list, ctx.svs)):
             out = _backward_impl(rs, sv, means3D, sh if has_sh else None, colors if has_col else None, opacities,
@@ -617,25 +623,29 @@ class _RasterizeViews(torch.autograd.Function):
                                  cov3D if has_cov else None, radii[v],
                                  None if grad_color is None else grad_color[v],
                                  None if grad_depth is None else grad_depth[v],
-                                 None if grad_alpha is None else grad_alpha[v], out=out, accumulate=v > 0)
+                                 None if grad_alpha is None else grad_alpha[v], out=out, accumulate=v > 0,
+                                 raw=ctx.raw)
         ctx.svs = None
         return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
-                out["rotations"], out["cov3D"], None, None)
+                out["rotations"], out["cov3D"], None, None, None)
 
 
 def rasterize_views(settings_list, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
-                    rotations=None, cov3D_precomp=None, exchange=None):
+                    rotations=None, cov3D_precomp=None, exchange=None, raw_inputs: int = 0):
     """Batched form of GaussianRasterizer(...)(...): returns stacked (color [V,3,H,W], radii [V,P],
     depth [V,1,H,W], alpha [V,1,H,W]); means2D.grad receives the SUM over views.  With
     ``exchange`` (gaussianip_b200.exchange.GradExchange) the input gradients returned by the backward
-    are already summed over the ranks of the exchange's group (reduction fused into the kernel)."""
+    are already summed over the ranks of the exchange's group (reduction fused into the kernel).
+    ``raw_inputs`` (bits _lib.RAW_OPACITY | RAW_SCALE | RAW_ROTATION): the flagged inputs are the model's raw
+    parameters (logits / log-scales / unnormalised quaternions); the kernels apply sigmoid / exp / normalize
+    and the returned gradients are with respect to the raw tensors (include/gsb.h GSB_RAW_*)."""
     if (shs is None) == (colors_precomp is None):
         raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                 cov3D_precomp, tuple(settings_list), exchange)
+                                 cov3D_precomp, tuple(settings_list), exchange, int(raw_inputs))
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

@@ -19,6 +19,7 @@ import math
 
 import torch
 
+from . import _lib
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
 
 SH_C0 = 0.28209479177387814
@@ -91,7 +92,7 @@ render_with_smaller_scale = render
 
 
 def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
-                 screenspace_points=None, exchange=None):
+                 screenspace_points=None, exchange=None, fused_activations: bool = False):
     """All views of one optimisation step in ONE call (additive API; the reference loops
     ``render`` over the views in Python, threestudio/systems/GaussianIP.py:154-159, 305-307).
 
@@ -101,7 +102,10 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
     over views directly.  Returns the ``render`` dictionary with a leading view axis:
     render [V,3,H,W], depth_3dgs / alpha_3dgs [V,1,H,W], radii_per_view [V,P], radii = max over
     views [P], visibility_filter = radii > 0.  ``exchange``: see rasterize_views (multi-GPU, gradients reduced
-    over ranks inside the backward kernel)."""
+    over ranks inside the backward kernel).  ``fused_activations``: hand the model's RAW parameters
+    (``pc._opacity``, ``pc._scaling``, ``pc._rotation`` — the reference's attribute names) to the kernels, which apply
+    sigmoid / exp / normalize themselves (gaussian_model.py:84-107) and return raw-parameter gradients: same
+    values as the getters + autograd to fp32 rounding, ~15 fewer torch kernels per step."""
     xyz = _get(pc, "get_xyz")
     if screenspace_points is None:
         screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
@@ -112,10 +116,19 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
     sh_degree = getattr(pc, "active_sh_degree", getattr(pc, "sh_degree", 0))
     settings = [_settings(cam, bg_color, scaling_modifier, sh_degree) for cam in cameras]
     scales = rotations = cov3D_precomp = None
+    raw = 0
     if pipe is not None and getattr(pipe, "compute_cov3D_python", False):
         cov3D_precomp = pc.get_covariance(scaling_modifier)
+    elif fused_activations:
+        scales, rotations = pc._scaling, pc._rotation
+        raw |= _lib.RAW_SCALE | _lib.RAW_ROTATION
     else:
         scales, rotations = _get(pc, "get_scaling"), _get(pc, "get_rotation")
+    if fused_activations:
+        opacities = pc._opacity
+        raw |= _lib.RAW_OPACITY
+    else:
+        opacities = _get(pc, "get_opacity")
     shs = colors_precomp = None
     if override_color is not None:
         colors_precomp = override_color
@@ -126,8 +139,8 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
     f = lambda t: None if t is None else t.float()
     image, radii_v, depth, alpha = rasterize_views(
         settings, means3D=xyz.float(), means2D=screenspace_points.float(), shs=f(shs),
-        colors_precomp=colors_precomp, opacities=_get(pc, "get_opacity").float(), scales=f(scales),
-        rotations=f(rotations), cov3D_precomp=cov3D_precomp, exchange=exchange)
+        colors_precomp=colors_precomp, opacities=opacities.float(), scales=f(scales),
+        rotations=f(rotations), cov3D_precomp=cov3D_precomp, exchange=exchange, raw_inputs=raw)
     radii = radii_v.max(dim=0).values
     return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii, "radii_per_view": radii_v, "depth_3dgs": depth, "alpha_3dgs": alpha}

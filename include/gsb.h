@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 1
+#define GSB_ABI_VERSION 2
 
 enum {
   GSB_OK = 0,
@@ -34,6 +34,15 @@ enum {
   GSB_E_CAPACITY = -3,    /* D (num_rendered) exceeded D_cap; re-run with a larger workspace */
   GSB_E_UNSUPPORTED = -4
 };
+
+/* Additive: the activations GaussianModel applies before every render call
+ * (gaussian_model.py:84-107: opacity = sigmoid(_opacity), scaling = exp(_scaling), rotation = normalize(_rotation))
+ * can be evaluated inside the per-Gaussian kernels instead of by ~15 torch kernels per step: with a bit set, the
+ * corresponding input holds the raw parameter, the forward activates it on load, and the backward returns the
+ * gradient with respect to the RAW parameter (chain rule applied after the sum over views). */
+#define GSB_RAW_OPACITY 1    /* opacities are logits */
+#define GSB_RAW_SCALE 2      /* scales are log-scales */
+#define GSB_RAW_ROTATION 4   /* rotations are unnormalised quaternions */
 
 /* The 12 fields of GaussianRasterizationSettings
  * (gaussiansplatting/gaussian_renderer/__init__.py:36-49) that reach the kernels. */
@@ -44,6 +53,7 @@ typedef struct GsbSettings {
   int32_t sh_degree;         /* active degree, 0..3 */
   int32_t prefiltered;       /* accepted for API parity; every call site passes False */
   int32_t debug;             /* !=0: synchronise + check after every kernel */
+  int32_t raw_inputs;        /* GSB_RAW_* bits: which inputs are the model's RAW parameters (0 = the reference's contract) */
   const float* bg;           /* [3]  device */
   const float* viewmatrix;   /* [16] device, column-major world->view (row-vector convention) */
   const float* projmatrix;   /* [16] device, column-major full projection */

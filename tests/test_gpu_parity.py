@@ -396,3 +396,62 @@ def test_speculative_step_redoes_on_overflow(cuda_device):
     assert all(w.pending is None for w in R._workspaces.values())
     got = util.run_gpu(scene, dev)
     assert (got["color"].cpu() - util.run_oracle(scene)["color"]).abs().max().item() <= FWD_ATOL
+
+
+class _RawModel:
+    """GaussianModel's getters (gaussian_model.py:84-107) over raw leaf parameters, reference attribute names."""
+
+    def __init__(self, scene, dev, deg):
+        g = torch.Generator().manual_seed(17)
+        P = scene.means3D.shape[0]
+        self.active_sh_degree = deg
+        leaf = lambda t: t.detach().clone().to(dev).requires_grad_(True)
+        self._xyz = leaf(scene.means3D)
+        self._features = leaf(scene.shs)
+        op = scene.opacities.clamp(1e-4, 1 - 1e-4)
+        self._opacity = leaf(torch.log(op / (1 - op)))
+        self._scaling = leaf(torch.log(scene.scales))
+        self._rotation = leaf(scene.rotations * (0.5 + torch.rand(P, 1, generator=g)))     # unnormalised
+    get_xyz = property(lambda s: s._xyz)
+    get_features = property(lambda s: s._features)
+    get_opacity = property(lambda s: torch.sigmoid(s._opacity))
+    get_scaling = property(lambda s: torch.exp(s._scaling))
+    get_rotation = property(lambda s: torch.nn.functional.normalize(s._rotation))
+
+    def leaves(self):
+        return {"xyz": self._xyz, "features": self._features, "opacity": self._opacity, "scaling": self._scaling,
+                "rotation": self._rotation}
+
+
+@pytest.mark.parametrize("deg,multistream", [(0, True), (2, True), (1, False)])
+def test_fused_activations_equal_torch_getters(cuda_device, deg, multistream):
+    """render_views(fused_activations=True): sigmoid / exp / normalize inside the kernels and raw-parameter
+    gradients out == the reference's getters + autograd around the operator."""
+    from gaussianip_b200 import rasterizer as R, renderer, synthetic
+    dev = cuda_device
+    H = W = 128
+    scene = util.humanoid_scene(P=8000, H=H, W=W, sh_degree=deg)
+    cams = synthetic.ahds_cameras(3, H, W, seed=6, device=dev)
+    g = torch.Generator().manual_seed(4)
+    wc, wd, wa = (torch.randn(3, c, H, W, generator=g).to(dev) for c in (3, 1, 1))
+    bg = torch.zeros(3, device=dev)
+    R.set_multistream(multistream)
+    try:
+        res = []
+        for fused in (False, True):
+            m = _RawModel(scene, dev, deg)
+            out = renderer.render_views(cams, m, None, bg, fused_activations=fused)
+            loss = (out["render"] * wc).sum() + (out["depth_3dgs"] * wd).sum() + (out["alpha_3dgs"] * wa).sum()
+            loss.backward()
+            res.append((out, {k: v.grad.clone() for k, v in m.leaves().items()},
+                        out["viewspace_points"].grad.clone()))
+    finally:
+        R.set_multistream(True)
+    (oa, ga, va), (ob, gb, vb) = res
+    # activations in-kernel may differ from torch's by an ulp: a radius can move by one pixel for ~1e-6 of the points
+    assert (oa["radii_per_view"] != ob["radii_per_view"]).float().mean().item() <= 1e-4
+    for k in ("render", "depth_3dgs", "alpha_3dgs"):
+        assert (oa[k] - ob[k]).abs().max().item() <= FWD_ATOL, k
+    for k in ga:
+        _grad_close(k, gb[k], ga[k])
+    _grad_close("viewspace", vb, va)

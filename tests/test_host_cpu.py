@@ -33,7 +33,7 @@ def test_library_exports_every_header_symbol(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.gsb_abi_version() == 1
+    assert lib.gsb_abi_version() == 2
     assert lib.gsb_strerror(0) == b"ok"
     assert b"invalid" in lib.gsb_strerror(-1)
 
