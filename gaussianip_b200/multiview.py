@@ -195,10 +195,21 @@ class ViewParallel:
         local views) and stacked outputs; loss_fn(local_view_indices, dict) -> scalar."""
         b = self.bucket
         local = shard_views(n_views, self.rank, self.world) if views is None else list(views)
+        # Nothing has to be summed on this rank after the single backward call when there is no NCCL bucket to
+        # fill (one rank, or the exchange already happened inside the kernel): leave .grad empty so autograd
+        # simply adopts the tensors the backward returns — no bucket zeroing, no accumulate kernels.  The
+        # gradients are then separate tensors (with the fused exchange: views of its buffer, valid until the
+        # next step's backward) instead of views of the flat bucket.
+        direct = self.exchange is not None or self.world == 1
 
         def body():
-            b.zero_()
-            b.attach()
+            if direct:
+                for p in b.params.values():
+                    p.grad = None
+                b.viewspace_points.grad = None
+            else:
+                b.zero_()
+                b.attach()
             if not local:
                 return (torch.zeros(self.n_points, dtype=torch.int32, device=b.device),
                         torch.zeros((), dtype=torch.float32, device=b.device))
@@ -223,4 +234,9 @@ class ViewParallel:
         all_reduce_radii_max(radii, self.group)
         if self.world > 1:
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
-        return {"loss": total, "radii": radii, "viewspace_grad": b.viewspace_grad(), "local_views": local}
+        if direct:
+            vg = b.viewspace_points.grad
+            vg = vg if vg is not None else torch.zeros_like(b.viewspace_points)
+        else:
+            vg = b.viewspace_grad()
+        return {"loss": total, "radii": radii, "viewspace_grad": vg, "local_views": local}

@@ -88,7 +88,9 @@ def run(fused):
         print("fused" if fused else "nccl", {k: round(m / c * 1e3, 1) for k, (m, c) in prof.items() if c}, flush=True)
     ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return out, vp.bucket.flat.clone(), float(ms.item())
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params.values()]
+                     + [out["viewspace_grad"].reshape(-1)]).clone()
+    return out, flat, float(ms.item())
 
 
 out_n, flat_n, ms_n = run(False)

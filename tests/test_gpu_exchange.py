@@ -24,6 +24,7 @@ def test_fused_exchange_equals_nccl_all_reduce(algo, extra):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if not lines:
+        assert "NVLS multicast is not available" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
         pytest.skip("fused exchange unavailable on this box: " + r.stdout[-300:])
     d = ast.literal_eval(lines[-1])
     assert d["radii_equal"] and d["replica_checksum_spread"] == 0.0

@@ -382,7 +382,7 @@ def test_speculative_step_redoes_on_overflow(cuda_device):
         out = vp.step_batched(3, render_views_fn, loss_fn, views=range(3))
         torch.cuda.synchronize()
         retries = sum(w.retries for w in R._workspaces.values()) - retries0
-        return out, {k: v.grad.clone() for k, v in params.items()}, vp.bucket.viewspace_grad().clone(), retries
+        return out, {k: v.grad.clone() for k, v in params.items()}, out["viewspace_grad"].clone(), retries
 
     out_a, grads_a, vs_a, _ = run(False)
     out_b, grads_b, vs_b, retries = run(True)
