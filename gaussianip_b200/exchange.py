@@ -37,6 +37,39 @@ _FIELDS = (("means3D", 3), ("means2D", 3), ("opacities", 1), ("shs", None), ("co
            ("rotations", 4), ("cov3D", 6))
 
 
+def plan_layout(P: int, K: int, present: Dict[str, bool]):
+    """Field offsets (in floats, every field 256 B aligned) of one half of the symmetric buffer.
+    Returns ({name: (offset, shape)}, total_floats)."""
+    off, layout = 0, {}
+    for name, w in _FIELDS:
+        if not present.get(name, False):
+            continue
+        shape = (P, K, 3) if name == "shs" else (P, w)
+        n = 1
+        for d in shape:
+            n *= d
+        layout[name] = (off, shape)
+        off += (n + 63) // 64 * 64
+    return layout, off
+
+
+def plan_ownership(P: int, layout, rank: int, world: int):
+    """owner_push: rank r owns rows [r * rows_per_rank, (r+1) * rows_per_rank) (the last rank also the tail);
+    rows_per_rank is a multiple of 32 so the 32 rows of a warp have one owner.  Returns (rows_per_rank,
+    [(offset_floats, count_floats)] of this rank's block in every field)."""
+    rows_per_rank = max((-(-P // world) + 31) // 32 * 32, 32)
+    r0 = min(rank * rows_per_rank, P)
+    r1 = P if rank == world - 1 else min(r0 + rows_per_rank, P)
+    segments = []
+    for name, (foff, shape) in layout.items():
+        w = 1
+        for d in shape[1:]:
+            w *= d
+        if r1 > r0 and w > 0:
+            segments.append((foff + r0 * w, (r1 - r0) * w))
+    return rows_per_rank, segments
+
+
 class GradExchange:
     def __init__(self, group=None, clone_outputs: bool = True, algorithm: str = "auto"):
         """clone_outputs=False hands the backward's consumers views of the symmetric buffer itself (valid until
@@ -83,16 +116,7 @@ class GradExchange:
         if key == self.key:
             return
         import torch.distributed._symmetric_memory as symm_mem
-        off, layout = 0, {}
-        for name, w in _FIELDS:
-            if not present.get(name, False):
-                continue
-            shape = (P, K, 3) if name == "shs" else (P, w)
-            n = 1
-            for d in shape:
-                n *= d
-            layout[name] = (off, shape)
-            off += (n + 63) // 64 * 64            # 256 B alignment of every field
+        layout, off = plan_layout(P, K, present)
         # two halves used alternately: the half of step k+1 is zeroed during step k and step k's closing barrier
         # tells every rank so, which saves the "everyone has zeroed" barrier in front of each kernel
         self.half = max(off, 64)
@@ -101,18 +125,7 @@ class GradExchange:
         if not getattr(self.hdl, "has_multicast_support", False) or not self.hdl.multicast_ptr:
             raise RuntimeError("NVLS multicast is not available on this system; use the NCCL exchange")
         self.offsets, self.key = layout, key
-        # ownership blocks (owner_push): contiguous row ranges, multiples of 32 rows so a warp has one owner
-        rpr = (-(-P // self.world) + 31) // 32 * 32
-        self.rows_per_rank = max(rpr, 32)
-        r0 = min(self.rank * self.rows_per_rank, P)
-        r1 = P if self.rank == self.world - 1 else min(r0 + self.rows_per_rank, P)
-        self.segments = []
-        for name, (foff, shape) in layout.items():
-            w = 1
-            for d in shape[1:]:
-                w *= d
-            if r1 > r0 and w > 0:
-                self.segments.append((foff + r0 * w, (r1 - r0) * w))
+        self.rows_per_rank, self.segments = plan_ownership(P, layout, self.rank, self.world)
         if self.mode == 3:
             import ctypes as C
             from . import _lib

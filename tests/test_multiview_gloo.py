@@ -130,3 +130,34 @@ def test_balanced_sharding_partitions_and_balances():
     assert shard_views_balanced([1.0, 1.0, 1.0], 0, 2) == [0]                         # ties broken by index,
     assert shard_views_balanced([1.0, 1.0, 1.0], 1, 2) == [1, 2]                      # dealt in snake order
     assert shard_views_balanced([], 0, 2) == []
+
+
+def test_exchange_plan_covers_every_row_once():
+    """Host-side planning of the fused exchange (exchange.py): field offsets are 16-byte aligned and the
+    ownership blocks of all ranks tile every field exactly, warp-aligned, for any rank count."""
+    from gaussianip_b200.exchange import plan_layout, plan_ownership
+    present = {"means3D": True, "means2D": True, "opacities": True, "shs": True, "colors": False, "scales": True,
+               "rotations": True, "cov3D": False}
+    for P, K in ((1_000_000, 1), (50_001, 4), (33, 16), (7, 1)):
+        layout, total = plan_layout(P, K, present)
+        assert set(layout) == {"means3D", "means2D", "opacities", "shs", "scales", "rotations"}
+        spans = sorted((off, off + int(torch.Size(shape).numel())) for off, shape in layout.values())
+        assert all(off % 64 == 0 for off, _ in spans) and spans[-1][1] <= total
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))                 # fields do not overlap
+        for world in (1, 2, 3, 4, 8, 16):
+            covered = {name: [] for name in layout}
+            rprs = set()
+            for rank in range(world):
+                rpr, segs = plan_ownership(P, layout, rank, world)
+                rprs.add(rpr)
+                assert rpr % 32 == 0
+                for off, cnt in segs:
+                    assert off % 4 == 0, "blocks must start 16-byte aligned for the vector stores"
+                    name = max((n for n in layout if layout[n][0] <= off), key=lambda n: layout[n][0])
+                    covered[name].append((off - layout[name][0], cnt))
+            assert len(rprs) == 1
+            for name, (off, shape) in layout.items():
+                n = int(torch.Size(shape).numel())
+                pieces = sorted(covered[name])
+                assert pieces[0][0] == 0 and sum(c for _, c in pieces) == n
+                assert all(a[0] + a[1] == b[0] for a, b in zip(pieces, pieces[1:]))  # contiguous, no gaps / overlap
