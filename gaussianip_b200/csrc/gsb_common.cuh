@@ -59,6 +59,15 @@ inline View make_view(const GsbSettings* s) {
   return v;
 }
 
+// exp() of the blend kernels: ex2.approx on x*log2(e), flush-to-zero.  __expf adds a range fix-up so that results
+// below 2^-126 come out as denormals (4 extra instructions per evaluation); such a Gaussian weight is ~1e-38,
+// its alpha is far below 1/255 and the pair is skipped either way, so the fix-up buys nothing here.
+__device__ __forceinline__ float exp_blend(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 // Activations of the raw model parameters (GSB_RAW_*), written the way torch evaluates them.
 __device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float4 act_normalize(float4 q, float* norm_out = nullptr) {

@@ -194,7 +194,7 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           f[i] = st[2][k[i]];
           dx[i] = a.x - pxf; dy[i] = a.y - pyf;
           const float power = -0.5f * (q[i].x * dx[i] * dx[i] + q[i].z * dy[i] * dy[i]) - q[i].y * dx[i] * dy[i];
-          G[i] = __expf(power);
+          G[i] = exp_blend(power);
           alpha[i] = fminf(ALPHA_CAP, q[i].w * G[i]);
           valid[i] = ((uint32_t)(base + k[i] + 1) <= my_last) && power <= 0.0f && alpha[i] >= ALPHA_MIN;
         }

@@ -136,7 +136,7 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
             ff[i] = st[2][k[i]];              // depth, r, g, b
             const float dx = a.x - pxf, dy = a.y - pyf;
             const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
-            al[i] = power <= 0.0f ? fminf(ALPHA_CAP, q.w * __expf(power)) : 0.0f;
+            al[i] = power <= 0.0f ? fminf(ALPHA_CAP, q.w * exp_blend(power)) : 0.0f;
           }
         }
 #pragma unroll
