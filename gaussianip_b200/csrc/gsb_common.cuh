@@ -68,6 +68,14 @@ __device__ __forceinline__ float exp_blend(float x) {
   return y;
 }
 
+// 1/x for x in [0.01, 1] (x = 1 - alpha, alpha <= 0.99): the bare MUFU.RCP; __fdividef wraps the same instruction in
+// a denormal-range fix-up (4 extra instructions) that cannot trigger here.
+__device__ __forceinline__ float rcp_blend(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Activations of the raw model parameters (GSB_RAW_*), written the way torch evaluates them.
 __device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float4 act_normalize(float4 q, float* norm_out = nullptr) {

@@ -209,7 +209,7 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           //   Bdot_i = T_final <bg, dL/dC> + sum_{j behind i} phi_j alpha_j T_j,
           // dL/dalpha_i = T_i phi_i - Bdot_i / (1 - alpha_i): the reference's five "colour behind"
           // recurrences collapse into ONE scalar (identical in exact arithmetic).
-          const float inv1ma = __fdividef(1.0f, 1.0f - alpha[i]);
+          const float inv1ma = rcp_blend(1.0f - alpha[i]);
           T *= inv1ma;
           const float w = alpha[i] * T;
           const float phi = f[i].y * gC0 + f[i].z * gC1 + f[i].w * gC2 + f[i].x * gD + gA;

@@ -67,11 +67,14 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   const int chunks = (n + 31) >> 5;
   const uint32_t* pl = point_list + range.x;
 
-  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f, A = 0.f;
+  // A pixel is "done" (saturated, or outside the image) exactly when T == 0: a live pixel always has
+  // T >= T_MIN, and with T = 0 every later test T*(1-alpha) >= T_MIN fails by itself, so the hit loop needs
+  // no separate flag.  T_live follows T while the pixel accumulates and keeps the last value afterwards
+  // (the transmittance the reference reports as final_T).
+  float T = inside ? 1.0f : 0.0f, T_live = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f, A = 0.f;
   uint32_t last = 0;
-  bool done = !inside;
 
-  if (chunks > 0 && !__all_sync(0xffffffffu, done)) {
+  if (chunks > 0 && __any_sync(0xffffffffu, T != 0.0f)) {
     float4 (*ring)[3][32] = s_rec[warp];
     auto issue = [&](int c, uint32_t gid) {      // stage chunk c (lane's instance) into the ring
       if (c < chunks) {
@@ -101,6 +104,7 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       __syncwarp();                              // ... and for every lane of the warp
       float4 (*st)[32] = ring[c & (STAGES - 1)];
       const int e = c * 32 + lane;
+      const bool done = T == 0.0f;
       const uint32_t alive = __ballot_sync(0xffffffffu, !done);
       if (alive != alive_prev) {
         alive_prev = alive;
@@ -141,27 +145,28 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
         }
 #pragma unroll
         for (int i = 0; i < HB; ++i) {
-          if (k[i] >= 0 && !done && al[i] >= ALPHA_MIN) {
+          if (k[i] >= 0 && al[i] >= ALPHA_MIN) {
             const float test_T = T * (1.0f - al[i]);
-            if (test_T < T_MIN) {
-              done = true;
-            } else {
+            const bool ok = test_T >= T_MIN;
+            if (ok) {
               const float w = al[i] * T;
               C0 += ff[i].y * w; C1 += ff[i].z * w; C2 += ff[i].w * w;
               Dz += ff[i].x * w; A += w;
-              T = test_T;
+              T_live = test_T;
               last = (uint32_t)(c * 32 + k[i] + 1);
             }
+            T = ok ? test_T : 0.0f;       // a saturating splat (or a finished pixel) leaves T at 0
           }
         }
       }
-      if (__all_sync(0xffffffffu, done)) break;
+      if (__all_sync(0xffffffffu, T == 0.0f)) break;
       __syncwarp();                              // ring slot c is free before it is refilled
     }
     cp_async_wait<0>();
   }
 
   if (inside) {
+    T = T_live;
     const size_t hw = (size_t)v.H * v.W;
     const size_t pix = (size_t)pix_y * v.W + pix_x;
     out_color[pix] = C0 + T * v.bg[0];
