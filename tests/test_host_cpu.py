@@ -32,6 +32,37 @@ def test_library_exports_every_header_symbol(lib):
     assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype in _lib.py has as many arguments as the declaration in include/gsb.h, pointers where the
+    header has pointers, and the struct mirrors have the header's size (guards against silent ABI drift)."""
+    from gaussianip_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "gsb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = dict(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(decls) == set(_lib.EXPORTS)
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        args = [] if params in ("", "void") else [a.strip() for a in params.split(",")]
+        restype, argtypes = _lib._PROTOS[name]
+        assert len(args) == len(argtypes), f"{name}: header has {len(args)} parameters, ctypes {len(argtypes)}"
+        for a, t in zip(args, argtypes):
+            is_ptr = "*" in a
+            t_is_ptr = t is C.c_void_p or t is C.c_char_p or issubclass(t, C._Pointer)
+            assert is_ptr == t_is_ptr, f"{name}: '{a}' vs {t}"
+            if not is_ptr:
+                want = {"int": C.c_int, "long long": C.c_longlong, "size_t": C.c_size_t, "float": C.c_float,
+                        "double": C.c_double}[" ".join(a.split()[:-1]).replace("const ", "")]
+                assert t is want, f"{name}: '{a}' vs {t}"
+    # struct GsbSettings: 9 x 4-byte scalars, padding to 8, 4 pointers
+    assert C.sizeof(_lib.GsbSettings) == 40 + 4 * C.sizeof(C.c_void_p)
+    m = re.search(r"typedef struct GsbSettings \{(.*?)\} GsbSettings;", src, flags=re.S)
+    fields = re.findall(r"(\w+)\s*(?:,|;)", re.sub(r"\b(int32_t|float|const)\b|\*", " ", m.group(1)))
+    assert fields == [f[0] for f in _lib.GsbSettings._fields_], fields
+    m = re.search(r"typedef struct GsbLayout \{(.*?)\} GsbLayout;", src, flags=re.S)
+    names = [n.strip() for grp in re.findall(r"size_t\s+([^;]+);", m.group(1)) for n in grp.split(",")]
+    assert names == [f[0] for f in _lib.GsbLayout._fields_]
+
+
 def test_abi_version_and_strerror(lib):
     assert lib.gsb_abi_version() == 2
     assert lib.gsb_strerror(0) == b"ok"
