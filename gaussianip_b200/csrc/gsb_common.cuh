@@ -18,7 +18,7 @@ constexpr float T_MIN = 0.0001f;
 // Per-Gaussian record gathered by the blend kernels: 48 B, 16 B aligned, three float4.
 struct __align__(16) Geom {
   float x, y, extx, exty;       // pixel centre, conservative half-extent of {alpha >= 1/255} in px
-  float ca, cb, cc, opacity;    // conic A, B, C, opacity
+  float ca, cb, cc, opacity;    // conic, pre-scaled: -0.5 log2e A, -log2e B, -0.5 log2e C (see gauss_exponent2); opacity
   float depth, r, g, b;         // view z, colour
 };
 static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
@@ -57,6 +57,21 @@ inline View make_view(const GsbSettings* s) {
   v.scale_mod = s->scale_modifier; v.sh_degree = s->sh_degree; v.raw = s->raw_inputs;
   v.bg = s->bg; v.view = s->viewmatrix; v.proj = s->projmatrix; v.campos = s->campos;
   return v;
+}
+
+// The Geom record stores the conic PRE-SCALED for the blend kernels: with qa = -0.5 log2(e) A, qb = -log2(e) B,
+// qc = -0.5 log2(e) C the Gaussian weight is G = 2^(qa dx^2 + qb dx dy + qc dy^2): five instructions and a bare
+// ex2 instead of eight plus the log2(e) multiply.  preprocess_bwd un-scales when it needs A, B, C.
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float CONIC_SCALE_AC = -0.5f * LOG2E;
+constexpr float CONIC_SCALE_B = -LOG2E;
+__device__ __forceinline__ float gauss_exponent2(float qa, float qb, float qc, float dx, float dy) {
+  return fmaf(qc * dy, dy, fmaf(qa, dx, qb * dy) * dx);
+}
+__device__ __forceinline__ float exp2_blend(float e) {     // 2^e, flush-to-zero (see exp_blend)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(e));
+  return y;
 }
 
 // exp() of the blend kernels: ex2.approx on x*log2(e), flush-to-zero.  __expf adds a range fix-up so that results

@@ -167,7 +167,7 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
         }
         float4* dst = reinterpret_cast<float4*>(geom + i);
         dst[0] = make_float4(pixx, pixy, ex, ey);
-        dst[1] = make_float4(cA, cB, cC, o);
+        dst[1] = make_float4(cA * CONIC_SCALE_AC, cB * CONIC_SCALE_B, cC * CONIC_SCALE_AC, o);
         dst[2] = make_float4(tz, r_, g_, b_);
         clamped[i] = cl;
         rect[i] = make_ushort4((unsigned short)minx, (unsigned short)miny, (unsigned short)maxx,

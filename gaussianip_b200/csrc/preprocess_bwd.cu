@@ -84,7 +84,8 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
   const float4* gp = reinterpret_cast<const float4*>(ggrad + i);
   const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
   // moments -> gradients of the screen-space mean (NDC units) and of the conic
-  const float4 con = reinterpret_cast<const float4*>(geom + i)[1];   // conA, conB, conC, opacity
+  float4 con = reinterpret_cast<const float4*>(geom + i)[1];         // pre-scaled conic, opacity
+  con.x *= 1.0f / CONIC_SCALE_AC; con.y *= 1.0f / CONIC_SCALE_B; con.z *= 1.0f / CONIC_SCALE_AC;   // back to A, B, C
   const float gx = -(con.x * g0.x + con.y * g0.y) * (0.5f * (float)v.W);
   const float gy = -(con.z * g0.y + con.y * g0.x) * (0.5f * (float)v.H);
   const float gA = -0.5f * g0.z, gB = -g0.w, gC = -0.5f * g1.x, gop = g1.y, gdepth = g1.z;

@@ -193,8 +193,8 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           q[i] = st[1][k[i]];
           f[i] = st[2][k[i]];
           dx[i] = a.x - pxf; dy[i] = a.y - pyf;
-          const float power = -0.5f * (q[i].x * dx[i] * dx[i] + q[i].z * dy[i] * dy[i]) - q[i].y * dx[i] * dy[i];
-          G[i] = exp_blend(power);
+          const float power = gauss_exponent2(q[i].x, q[i].y, q[i].z, dx[i], dy[i]);   // log2 of the weight
+          G[i] = exp2_blend(power);
           alpha[i] = fminf(ALPHA_CAP, q[i].w * G[i]);
           valid[i] = ((uint32_t)(base + k[i] + 1) <= my_last) && power <= 0.0f && alpha[i] >= ALPHA_MIN;
         }

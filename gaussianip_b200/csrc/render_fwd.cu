@@ -136,11 +136,11 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           al[i] = 0.0f;
           if (k[i] >= 0) {
             const float4 a = st[0][k[i]];     // x, y, -, -
-            const float4 q = st[1][k[i]];     // conA, conB, conC, opacity
+            const float4 q = st[1][k[i]];     // pre-scaled conic (qa, qb, qc), opacity
             ff[i] = st[2][k[i]];              // depth, r, g, b
             const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
-            al[i] = power <= 0.0f ? fminf(ALPHA_CAP, q.w * exp_blend(power)) : 0.0f;
+            const float e2 = gauss_exponent2(q.x, q.y, q.z, dx, dy);      // log2 of the Gaussian weight
+            al[i] = e2 <= 0.0f ? fminf(ALPHA_CAP, q.w * exp2_blend(e2)) : 0.0f;
           }
         }
 #pragma unroll

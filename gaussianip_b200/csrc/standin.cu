@@ -48,9 +48,9 @@ standin_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __rest
     for (int j = 0; !done && j < cnt; ++j) {
       const float4 a = s_a[j], q = s_q[j], f = s_f[j];
       const float dx = a.x - pxf, dy = a.y - pyf;
-      const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
+      const float power = gauss_exponent2(q.x, q.y, q.z, dx, dy);   // log2 of the weight (pre-scaled conic)
       if (power > 0.0f) continue;
-      const float alpha = fminf(ALPHA_CAP, q.w * __expf(power));
+      const float alpha = fminf(ALPHA_CAP, q.w * exp2_blend(power));
       if (alpha < ALPHA_MIN) continue;
       const float test_T = T * (1.0f - alpha);
       if (test_T < T_MIN) { done = true; continue; }
@@ -111,9 +111,9 @@ standin_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __rest
       if (pos > my_last) continue;
       const float4 a = s_a[j], q = s_q[j], f = s_f[j];
       const float dx = a.x - pxf, dy = a.y - pyf;
-      const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
+      const float power = gauss_exponent2(q.x, q.y, q.z, dx, dy);   // log2 of the weight (pre-scaled conic)
       if (power > 0.0f) continue;
-      const float G = __expf(power);
+      const float G = exp2_blend(power);
       const float alpha = fminf(ALPHA_CAP, q.w * G);
       if (alpha < ALPHA_MIN) continue;
       T = T / (1.0f - alpha);

@@ -65,7 +65,7 @@ typedef struct GsbSettings {
  * `scratch` is transient within one call and may be shared by all calls on one stream. */
 typedef struct GsbLayout {
   size_t saved_bytes;
-  size_t off_geom;        /* P x 48 B  GsbGeom record {x,y,extx,exty | conA,conB,conC,opacity | depth,r,g,b} */
+  size_t off_geom;        /* P x 48 B  GsbGeom record {x,y,extx,exty | qa,qb,qc (conic scaled by -0.5log2e,-log2e,-0.5log2e),opacity | depth,r,g,b} */
   size_t off_clamped;     /* P x u8    SH clamp mask (bit c: channel c clamped at 0) */
   size_t off_counts;      /* 8 x u32   [0]=D (num_rendered) [1]=overflow flag [2]=#visible [3]=max tiles per Gaussian */
   size_t off_point_list;  /* D_cap x u32  Gaussian index per sorted instance */

@@ -72,7 +72,10 @@ def test_forward_exact_and_tolerance(cuda_device, name, mode):
     vis = g.visible
     assert torch.equal(geom[vis][:, 0:2], g.xy[vis]), "pixel centres differ"
     assert torch.equal(geom[vis][:, 8], g.depth[vis]), "depths differ"
-    torch.testing.assert_close(geom[vis][:, [4, 5, 6]], g.conic[vis], rtol=1e-6, atol=0)
+    # the record holds the conic pre-scaled for the blend kernels: (-0.5 log2e A, -log2e B, -0.5 log2e C)
+    log2e = 1.4426950408889634
+    conic_scale = torch.tensor([-0.5 * log2e, -log2e, -0.5 * log2e], dtype=torch.float32)
+    torch.testing.assert_close(geom[vis][:, [4, 5, 6]], g.conic[vis] * conic_scale, rtol=1e-6, atol=0)
     torch.testing.assert_close(geom[vis][:, [9, 10, 11]], g.rgb[vis], rtol=1e-5, atol=1e-6)
     # images
     assert (color.cpu() - ref["color"]).abs().max().item() <= FWD_ATOL
