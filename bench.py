@@ -45,9 +45,10 @@ def parse():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--views", type=int, default=4, help="views per step per GPU")
     ap.add_argument("--sh-degree", type=int, default=0)
-    ap.add_argument("--variant", default="native", choices=["native", "standin"],
+    ap.add_argument("--variant", default="native", choices=["native", "standin", "packed_bwd"],
                     help="standin = reference-STRUCTURE kernels of csrc/standin.cu + 64-bit key sort + per-view "
-                         "Python loop, for context only (never the reference, never the product)")
+                         "Python loop, for context only (never the reference, never the product); packed_bwd = "
+                         "EXPERIMENTAL backward with a packed shared-memory reduction (not validated on hardware yet)")
     ap.add_argument("--view-sharding", default="interleaved", choices=["balanced", "interleaved"],
                     help="N>1: how the step's world x views cameras are dealt to the ranks")
     ap.add_argument("--exchange-algo", default="auto", choices=["auto", "push_all", "owner_push"])
@@ -283,6 +284,8 @@ def main():
     if standin:
         rasterizer.set_blend_variant("standin")
         rasterizer.set_binning_mode("flat64", dev)
+    elif a.variant == "packed_bwd":
+        rasterizer.set_blend_variant("packed_bwd")
 
     w_color = torch.stack([w[0] for w in weights])
     w_depth = torch.stack([w[1] for w in weights])
@@ -493,7 +496,8 @@ def main():
         cpu = {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     line = {"variant": "reference-STRUCTURE stand-in (csrc/standin.cu + flat 64-bit sort + per-view loop); NOT the "
-                       "reference and NOT the product path"} if standin else {}
+                       "reference and NOT the product path"} if standin else (
+        {"variant": "EXPERIMENTAL packed-reduction backward (gsb_set_blend_variant(2))"} if a.variant == "packed_bwd" else {})
     line.update({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",

@@ -165,7 +165,7 @@ int gsb_adam_step(int n_groups, float* const* params, const float* const* grads,
 }
 
 int gsb_set_blend_variant(int variant) {
-  if (variant != 0 && variant != 1) return GSB_E_INVALID;
+  if (variant < 0 || variant > 2) return GSB_E_INVALID;
   g_blend_variant.store(variant);
   return GSB_OK;
 }
@@ -264,7 +264,8 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
   return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order),
                            at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
-                           at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
+                           at<GGrad>(scratch, L.off_ggrad), g_blend_variant.load() == 2, s->debug != 0,
+                           (cudaStream_t)stream);
 }
 
 int gsb_preprocess_bwd_views(int V, const GsbSettings* const* settings, int P, int K, const float* means3D,

@@ -149,7 +149,7 @@ int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_lis
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
                       const float* final_T, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                      GGrad* ggrad, bool debug, cudaStream_t st);
+                      GGrad* ggrad, bool packed, bool debug, cudaStream_t st);
 
 // reference-structure stand-in blend kernels (standin.cu; measurement context and cross-check only)
 int launch_standin_fwd(const View& v, const Geom* geom, const uint32_t* point_list, const uint2* ranges,

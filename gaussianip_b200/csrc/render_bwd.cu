@@ -32,6 +32,21 @@ constexpr int STAGES = GSB_BWD_STAGES;
 #endif
 constexpr int BH = GSB_BWD_HB;       // hits evaluated together
 
+// EXPERIMENTAL variant (gsb_set_blend_variant(2), not the default, not yet validated on hardware — DESIGN.md §8.1):
+// instead of reducing every hit's ten partial sums over the 32 lanes with the butterfly (51 instructions for, on
+// average, 7.4 useful lanes), the lanes that actually contribute append their ten values to a packed per-warp slab
+// in shared memory, one segment per hit; when the slab fills up (and at the end) lanes (g, j) = (lane / 10, lane % 10)
+// sum component j of segment 3 r + g sequentially and issue the red.  Segments of different hits are independent,
+// so three hits are reduced per pass.
+#ifndef GSB_BWD_SLAB
+#define GSB_BWD_SLAB 40
+#endif
+constexpr int SLAB = GSB_BWD_SLAB;     // packed (pixel, hit) pairs per warp between two reductions (>= 32)
+constexpr int SLAB_STRIDE = 11;        // floats per pair: 10 used, odd stride keeps the stores conflict-free
+constexpr int SEG_MAX = 30;            // hits per reduction (three at a time)
+static_assert(SLAB >= 32, "one hit can contribute 32 pairs");
+constexpr size_t PACKED_WARP_BYTES = (size_t)SLAB * SLAB_STRIDE * 4 + (SEG_MAX + 2) * 4 + SEG_MAX * 4;
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -74,6 +89,7 @@ __device__ __forceinline__ float butterfly12(const float (&v)[12], int lane) {
   return r;
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(WARPS * 32)
 render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
@@ -85,11 +101,17 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
   uint32_t (*s_gid)[STAGES][32] =
       reinterpret_cast<uint32_t (*)[STAGES][32]>(smem_dyn + WARPS * STAGES * 3 * 32);
+  // PACKED only: per-warp slab + segment table behind the rings
+  char* packed_base = reinterpret_cast<char*>(smem_dyn) + (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
 
   const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  float* slab = reinterpret_cast<float*>(packed_base + (size_t)warp * PACKED_WARP_BYTES);
+  int* seg_start = reinterpret_cast<int*>(slab + SLAB * SLAB_STRIDE);        // [SEG_MAX + 2]
+  uint32_t* seg_gid = reinterpret_cast<uint32_t*>(seg_start + SEG_MAX + 2);  // [SEG_MAX]
+  int n_pairs = 0, n_seg = 0;                                                // warp-uniform
   const int pix_x = tx * TILE_X + wx + (lane & 7);
   const int pix_y = ty * TILE_Y + wy + (lane >> 3);
   const bool inside = pix_x < v.W && pix_y < v.H;
@@ -137,6 +159,23 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
     if (c >= chunks) return 0u;
     const int e = (chunks - 1 - c) * 32 + lane;
     return e < n ? pl[e] : 0u;
+  };
+  // PACKED: reduce the slab's segments (one per hit) and send them out; three hits per pass
+  auto flush = [&]() {
+    if (lane == 0) seg_start[n_seg] = n_pairs;          // end sentinel
+    __syncwarp();
+    const int grp = lane / 10, comp = lane - grp * 10;    // lanes 30, 31 (grp 3) idle
+    for (int h0 = 0; h0 < n_seg; h0 += 3) {
+      const int h = h0 + grp;
+      if (grp < 3 && h < n_seg) {
+        const int a = seg_start[h], b = seg_start[h + 1];
+        float sum = 0.0f;
+        for (int sl = a; sl < b; ++sl) sum += slab[sl * SLAB_STRIDE + comp];
+        if (sum != 0.0f) atomicAdd(reinterpret_cast<float*>(ggrad + seg_gid[h]) + comp, sum);
+      }
+    }
+    __syncwarp();
+    n_pairs = 0; n_seg = 0;
   };
 #pragma unroll
   for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_gid(c));
@@ -230,6 +269,23 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
           g[i][9] = w * gC2;
         }
       }
+      if (PACKED) {
+#pragma unroll
+        for (int i = 0; i < BH; ++i) {
+          const uint32_t vb = __ballot_sync(0xffffffffu, valid[i]);
+          if (!vb) continue;
+          const int nv = __popc(vb);
+          if (n_pairs + nv > SLAB || n_seg == SEG_MAX) flush();
+          if (lane == 0) { seg_start[n_seg] = n_pairs; seg_gid[n_seg] = gring[c & (STAGES - 1)][k[i]]; }
+          if (valid[i]) {
+            float* dst = slab + (n_pairs + __popc(vb & ((1u << lane) - 1u))) * SLAB_STRIDE;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) dst[j] = g[i][j];
+          }
+          n_pairs += nv; ++n_seg;
+        }
+        continue;
+      }
       const int slot = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
       const bool writer = !(lane & 1) && !((lane & 4) && (lane & 2)) && slot < 10;
       // (direct per-lane atomics for splats that only graze the warp were measured slower:
@@ -250,6 +306,7 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
     }
     __syncwarp();
   }
+  if (PACKED && n_seg) flush();
   cp_async_wait<0>();
 #ifdef GSB_BWD_STATS
   if (lane == 0) {
@@ -266,7 +323,7 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
                       const float* final_T, const float* dL_dcolor, const float* dL_ddepth,
-                      const float* dL_dalpha, GGrad* ggrad, bool debug, cudaStream_t st) {
+                      const float* dL_dalpha, GGrad* ggrad, bool packed, bool debug, cudaStream_t st) {
   GSB_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)P * sizeof(GGrad), st));
   const int T = v.gx * v.gy;
   if (T == 0 || P == 0) return GSB_OK;
@@ -274,16 +331,24 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
 #define GSB_BWD_SMEM_PAD 0
 #endif
   // (padding = an occupancy cap for tuning sweeps: shared memory not used by CTAs stays L1)
-  constexpr size_t smem = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t)) + GSB_BWD_SMEM_PAD;
+  constexpr size_t smem_ring = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
+  const size_t smem = smem_ring + (packed ? (size_t)WARPS * PACKED_WARP_BYTES : 0) + GSB_BWD_SMEM_PAD;
   static bool configured[64] = {};   // the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(smem_ring + GSB_BWD_SMEM_PAD)));
+    GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(smem_ring + WARPS * PACKED_WARP_BYTES + GSB_BWD_SMEM_PAD)));
     configured[dev & 63] = true;
   }
-  render_bwd_kernel<<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
-                                              dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
+  if (packed)
+    render_bwd_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
+                                                         dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
+  else
+    render_bwd_kernel<false><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
+                                                          dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
   GSB_POST_LAUNCH(debug, st, "render_bwd_kernel");
 #ifdef GSB_BWD_STATS
   {

@@ -257,7 +257,9 @@ int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, c
 /* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
  *   0  native kernels (the product path);
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
- *      culling, per-pixel global atomics — for measurement context and as a GPU cross-check only. */
+ *      culling, per-pixel global atomics — for measurement context and as a GPU cross-check only;
+ *   2  EXPERIMENTAL: native forward + backward with a packed shared-memory reduction instead of the per-hit
+ *      shuffle butterfly (csrc/render_bwd.cu, PACKED); not validated on hardware yet. */
 int gsb_set_blend_variant(int variant);
 
 /* Test / measurement helpers. */

@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): bit-exact radii / sort keys / tile ranges / instance order /
 per-pixel contributor counts; forward colour, depth, alpha within 1e-5 absolute (fp32);
 gradients within 1e-4 relative."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -458,3 +460,22 @@ def test_fused_activations_equal_torch_getters(cuda_device, deg, multistream):
     for k in ga:
         _grad_close(k, gb[k], ga[k])
     _grad_close("viewspace", vb, va)
+
+
+@pytest.mark.skipif(os.environ.get("GSB_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variant, not validated on hardware yet (set GSB_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("name", ["sh0_small", "big_splats", "dense_long_lists", "sh3"])
+def test_experimental_packed_backward_tolerance(cuda_device, name):
+    """The packed-reduction backward (gsb_set_blend_variant(2)) must meet the same gradient bar as the default."""
+    from gaussianip_b200 import rasterizer as R
+    scene = util.humanoid_scene(**SCENES[name])
+    w = util.loss_weights(scene.H, scene.W)
+    ref = util.run_oracle(scene, grads=w, requires_grad=True)
+    R.set_blend_variant("packed_bwd")
+    try:
+        got = util.run_gpu(scene, cuda_device, grads=w, requires_grad=True, debug=True)
+    finally:
+        R.set_blend_variant("native")
+    for k, rg in ref["grads"].items():
+        if rg is not None:
+            _grad_close(k, got["grads"][k], rg)
