@@ -333,15 +333,18 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
   // (padding = an occupancy cap for tuning sweeps: shared memory not used by CTAs stays L1)
   constexpr size_t smem_ring = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
   const size_t smem = smem_ring + (packed ? (size_t)WARPS * PACKED_WARP_BYTES : 0) + GSB_BWD_SMEM_PAD;
-  static bool configured[64] = {};   // the attribute is per device
+  static bool configured[64] = {}, configured_packed[64] = {};   // the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
+  if (!packed && !configured[dev & 63]) {
     GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(smem_ring + GSB_BWD_SMEM_PAD)));
+    configured[dev & 63] = true;
+  }
+  if (packed && !configured_packed[dev & 63]) {
     GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(smem_ring + WARPS * PACKED_WARP_BYTES + GSB_BWD_SMEM_PAD)));
-    configured[dev & 63] = true;
+    configured_packed[dev & 63] = true;
   }
   if (packed)
     render_bwd_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
