@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--variant", default="native", choices=["native", "standin", "packed_bwd"],
                     help="standin = reference-STRUCTURE kernels of csrc/standin.cu + 64-bit key sort + per-view "
                          "Python loop, for context only (never the reference, never the product); packed_bwd = "
-                         "EXPERIMENTAL backward with a packed shared-memory reduction (not validated on hardware yet)")
+                         "EXPERIMENTAL backward with a packed shared-memory reduction (parity-checked on one scene, not benchmarked)")
     ap.add_argument("--view-sharding", default="interleaved", choices=["balanced", "interleaved"],
                     help="N>1: how the step's world x views cameras are dealt to the ranks")
     ap.add_argument("--exchange-algo", default="auto", choices=["auto", "push_all", "owner_push"])

@@ -32,7 +32,8 @@ constexpr int STAGES = GSB_BWD_STAGES;
 #endif
 constexpr int BH = GSB_BWD_HB;       // hits evaluated together
 
-// EXPERIMENTAL variant (gsb_set_blend_variant(2), not the default, not yet validated on hardware — DESIGN.md §8.1):
+// EXPERIMENTAL variant (gsb_set_blend_variant(2), not the default; passed gradient parity on one scene, not yet
+// benchmarked — DESIGN.md §8.1):
 // instead of reducing every hit's ten partial sums over the 32 lanes with the butterfly (51 instructions for, on
 // average, 7.4 useful lanes), the lanes that actually contribute append their ten values to a packed per-warp slab
 // in shared memory, one segment per hit; when the slab fills up (and at the end) lanes (g, j) = (lane / 10, lane % 10)

@@ -334,8 +334,8 @@ def stats() -> dict:
 def set_blend_variant(name: str) -> None:
     """'native' (default, the product kernels), 'standin' (reference-STRUCTURE blend kernels of
     csrc/standin.cu, for measurement context and GPU cross-checks only) or 'packed_bwd' (EXPERIMENTAL
-    backward with a packed shared-memory reduction instead of the per-hit butterfly; not validated on
-    hardware yet — DESIGN.md §8.1)."""
+    backward with a packed shared-memory reduction instead of the per-hit butterfly; parity-checked on
+    one scene only, not benchmarked — DESIGN.md §8.1)."""
     _lib.check(_lib.load().gsb_set_blend_variant({"native": 0, "standin": 1, "packed_bwd": 2}[name]),
                "gsb_set_blend_variant")
 

@@ -259,7 +259,7 @@ int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, c
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
  *      culling, per-pixel global atomics — for measurement context and as a GPU cross-check only;
  *   2  EXPERIMENTAL: native forward + backward with a packed shared-memory reduction instead of the per-hit
- *      shuffle butterfly (csrc/render_bwd.cu, PACKED); not validated on hardware yet. */
+ *      shuffle butterfly (csrc/render_bwd.cu, PACKED); parity-checked on one scene only, not benchmarked. */
 int gsb_set_blend_variant(int variant);
 
 /* Test / measurement helpers. */
