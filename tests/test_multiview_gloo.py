@@ -161,3 +161,55 @@ def test_exchange_plan_covers_every_row_once():
                 pieces = sorted(covered[name])
                 assert pieces[0][0] == 0 and sum(c for _, c in pieces) == n
                 assert all(a[0] + a[1] == b[0] for a, b in zip(pieces, pieces[1:]))  # contiguous, no gaps / overlap
+
+
+def _run_step_batched(group=None):
+    params = {k: t.clone().requires_grad_(True) for k, t in _make_params().items()}
+    vp = multiview.ViewParallel(params, P, group)
+
+    def render_views_fn(views, vsp):
+        outs = [_render(params, v, vsp) for v in views]
+        return {"render": torch.stack([o["render"] for o in outs]),
+                "radii": torch.stack([o["radii"] for o in outs]).max(dim=0).values}
+
+    def loss_fn(views, out):
+        return sum((out["render"][i] ** 2).sum() * (0.5 + v) for i, v in enumerate(views))
+
+    res = vp.step_batched(V, render_views_fn, loss_fn)
+    grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+    return res, grads
+
+
+def _worker_batched(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res, grads = _run_step_batched()
+        ret[rank] = {"grads": grads, "vg": res["viewspace_grad"].clone(), "radii": res["radii"].clone(),
+                     "loss": res["loss"].clone()}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_batched_step_direct_gradients_and_two_ranks_agree_with_the_per_view_loop():
+    """step_batched on one rank adopts the backward's tensors (no bucket); on two ranks it fills and all-reduces
+    the bucket: both must equal the per-view step()."""
+    vp1, res1, *_ = _run_step()                               # per-view loop, bucket
+    ref = {k: vp1.bucket.views[k].clone() for k in vp1.bucket.params}
+    res_b, grads_b = _run_step_batched()                      # world 1: direct mode
+    for k in ref:
+        torch.testing.assert_close(grads_b[k], ref[k], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(res_b["viewspace_grad"], res1["viewspace_grad"], rtol=1e-4, atol=1e-4)
+    assert torch.equal(res_b["radii"], res1["radii"])
+    torch.testing.assert_close(res_b["loss"], res1["loss"], rtol=1e-5, atol=1e-5)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_batched, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in (0, 1):
+        for k in ref:
+            torch.testing.assert_close(ret[r]["grads"][k], ref[k], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ret[r]["vg"], res1["viewspace_grad"], rtol=1e-4, atol=1e-4)
+        assert torch.equal(ret[r]["radii"], res1["radii"])
+        torch.testing.assert_close(ret[r]["loss"], res1["loss"], rtol=1e-5, atol=1e-5)
