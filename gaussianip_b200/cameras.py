@@ -91,26 +91,28 @@ def cameras_from_c2w(c2ws, fovys, height, width, device="cuda"):
     threestudio/systems/GaussianIP.py:155; a pageable per-tensor upload would also block the host
     until the stream drains).  Values are identical to Camera(c2w, fovy, height, width)."""
     n = len(c2ws)
-    stage = torch.empty(n, 51, dtype=torch.float32)
+    fovys = [float(f) for f in fovys]
+    # batched host algebra (one LAPACK call for all inversions); values identical to the per-camera code
+    c2w = np.stack([np.asarray(c.detach().cpu() if torch.is_tensor(c) else c, dtype=np.float64) for c in c2ws])
+    w2c = np.linalg.inv(c2w)
+    w2c[:, 1:3, :3] *= -1.0
+    w2c[:, :3, 3] *= -1.0
+    view = np.ascontiguousarray(np.swapaxes(w2c, 1, 2))
+    fovxs = [focal2fov(fov2focal(f, height), width) for f in fovys]
+    proj = np.stack([projection_matrix(0.01, 100.0, fx, fy).T for fx, fy in zip(fovxs, fovys)])
+    full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
+    center = np.linalg.inv(view)[:, 3, :3]
+    rows = np.concatenate((view.reshape(n, 16), proj.reshape(n, 16), full.reshape(n, 16), center), axis=1)
+    stage = torch.from_numpy(rows.astype(np.float32))
     if torch.device(device).type == "cuda":
         stage = stage.pin_memory()
     cams = []
-    for i, (c2w, fovy) in enumerate(zip(c2ws, fovys)):
+    for fovx, fovy in zip(fovxs, fovys):
         cam = Camera.__new__(Camera)
-        fovy = float(fovy)
-        cam.FoVx, cam.FoVy = focal2fov(fov2focal(fovy, height), width), fovy
+        cam.FoVx, cam.FoVy = fovx, fovy
         cam.image_height, cam.image_width = int(height), int(width)
         cam.zfar, cam.znear, cam.trans, cam.scale = 100.0, 0.01, torch.zeros(3), 1.0
         cam.data_device = torch.device(device)
-        view = _w2c_from_c2w(c2w).T
-        proj = projection_matrix(cam.znear, cam.zfar, cam.FoVx, cam.FoVy).T
-        full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
-        center = np.linalg.inv(view)[3, :3]
-        row = stage[i]
-        row[0:16] = torch.from_numpy(view.reshape(-1).astype(np.float32))
-        row[16:32] = torch.from_numpy(proj.reshape(-1).astype(np.float32))
-        row[32:48] = torch.from_numpy(full.reshape(-1).astype(np.float32))
-        row[48:51] = torch.from_numpy(center.astype(np.float32))
         cams.append(cam)
     dev_buf = stage.to(device, non_blocking=True)
     for i, cam in enumerate(cams):
