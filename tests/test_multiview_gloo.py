@@ -156,6 +156,14 @@ def test_exchange_plan_covers_every_row_once():
                     name = max((n for n in layout if layout[n][0] <= off), key=lambda n: layout[n][0])
                     covered[name].append((off - layout[name][0], cnt))
             assert len(rprs) == 1
+            # the kernel's owner rule (csrc/preprocess_bwd.cu, MODE 3): owner = min(first_row_of_warp / rpr, world - 1)
+            rpr = rprs.pop()
+            w3 = 3                                                   # means3D rows are 3 floats wide
+            blocks = [plan_ownership(P, {"means3D": layout["means3D"]}, r, world)[1] for r in range(world)]
+            for first in range(0, P, 32):
+                owner = min(first // rpr, world - 1)
+                (off, cnt), = blocks[owner] or [(None, 0)]
+                assert off is not None and off <= layout["means3D"][0] + first * w3 < off + cnt, (P, world, first)
             for name, (off, shape) in layout.items():
                 n = int(torch.Size(shape).numel())
                 pieces = sorted(covered[name])
