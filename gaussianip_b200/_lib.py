@@ -11,7 +11,7 @@ LIB_PATH = _PKG / "libgsb.so"
 GSB_OK, GSB_E_INVALID, GSB_E_CUDA, GSB_E_CAPACITY, GSB_E_UNSUPPORTED = 0, -1, -2, -3, -4
 BIN_TWO_LEVEL, BIN_FLAT64 = 0, 1
 MAX_VIEWS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 RAW_OPACITY, RAW_SCALE, RAW_ROTATION = 1, 2, 4
 
 
@@ -61,6 +61,8 @@ _PROTOS = {
     "gsb_launch_count": (C.c_longlong, []),
     "gsb_adam_step": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_longlong,
                                 C.c_float, C.c_longlong, _P, _P, _P, _P, _P, _P]),
+    "gsb_adam_step_groups": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, _P,
+                                       C.c_float, C.c_longlong, _P, _P, _P, _P, _P, _P]),
     "gsb_set_blend_variant": (C.c_int, [C.c_int]),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "gsb_exchange_config": (C.c_int, [C.c_int, C.c_int, C.c_longlong, _P]),

@@ -20,7 +20,8 @@ struct AdamBatch {
   long long n[GSB_ADAM_MAX_GROUPS];
   long long first_block[GSB_ADAM_MAX_GROUPS + 1];   // blocks of group k: [first_block[k], first_block[k+1])
   float step_size[GSB_ADAM_MAX_GROUPS];              // lr / (1 - beta1^t)
-  float beta1, beta2, eps, bc2_sqrt, grad_scale;     // grad_scale multiplies g first (AMP unscale), 1 = off
+  float bc2_sqrt[GSB_ADAM_MAX_GROUPS];               // sqrt(1 - beta2^t), t = the group's own step count
+  float beta1, beta2, eps, grad_scale;               // grad_scale multiplies g first (AMP unscale), 1 = off
   float omb1, omb2;                                  // 1 - beta, rounded from double as torch does
   // densification statistics (optional, stats_n = 0 disables): one extra range of blocks
   long long stats_n;
@@ -35,11 +36,12 @@ constexpr int ADAM_THREADS = 256;
 constexpr int ADAM_VEC = 4;
 constexpr int ADAM_PER_BLOCK = ADAM_THREADS * ADAM_VEC;
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float step_size, const AdamBatch& B) {
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float step_size, float bc2_sqrt,
+                                         const AdamBatch& B) {
   g *= B.grad_scale;
   m = m + (g - m) * B.omb1;                                 // exp_avg.lerp_(grad, 1 - beta1)
   v = v * B.beta2 + B.omb2 * g * g;                         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-  const float denom = sqrtf(v) / B.bc2_sqrt + B.eps;
+  const float denom = sqrtf(v) / bc2_sqrt + B.eps;
   p = p - step_size * (m / denom);                          // param.addcdiv_(exp_avg, denom, -step_size)
 }
 
@@ -70,42 +72,44 @@ adam_stats_kernel(AdamBatch B) {
   const float* g = B.g[k] + base;
   float* m = B.m[k] + base;
   float* v = B.v[k] + base;
-  const float ss = B.step_size[k];
+  const float ss = B.step_size[k], bq = B.bc2_sqrt[k];
   const bool vec = base + ADAM_VEC <= n &&
                    (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
   if (vec) {
     float4 P4 = *reinterpret_cast<float4*>(p), M4 = *reinterpret_cast<float4*>(m), V4 = *reinterpret_cast<float4*>(v);
     const float4 G4 = *reinterpret_cast<const float4*>(g);
-    adam_one(P4.x, G4.x, M4.x, V4.x, ss, B); adam_one(P4.y, G4.y, M4.y, V4.y, ss, B);
-    adam_one(P4.z, G4.z, M4.z, V4.z, ss, B); adam_one(P4.w, G4.w, M4.w, V4.w, ss, B);
+    adam_one(P4.x, G4.x, M4.x, V4.x, ss, bq, B); adam_one(P4.y, G4.y, M4.y, V4.y, ss, bq, B);
+    adam_one(P4.z, G4.z, M4.z, V4.z, ss, bq, B); adam_one(P4.w, G4.w, M4.w, V4.w, ss, bq, B);
     *reinterpret_cast<float4*>(p) = P4; *reinterpret_cast<float4*>(m) = M4; *reinterpret_cast<float4*>(v) = V4;
   } else {
-    for (int j = 0; j < ADAM_VEC && base + j < n; ++j) adam_one(p[j], g[j], m[j], v[j], ss, B);
+    for (int j = 0; j < ADAM_VEC && base + j < n; ++j) adam_one(p[j], g[j], m[j], v[j], ss, bq, B);
   }
 }
 
 }  // namespace
 
 int launch_adam_stats(int G, float* const* p, const float* const* g, float* const* m, float* const* v,
-                      const long long* n, const float* lr, double beta1, double beta2, double eps, long long step,
-                      float grad_scale, long long stats_n, const float* viewspace_grad, const int32_t* radii,
+                      const long long* n, const float* lr, double beta1, double beta2, double eps,
+                      const long long* steps, float grad_scale, long long stats_n, const float* viewspace_grad, const int32_t* radii,
                       float* xyz_gradient_accum, float* denom, float* max_radii2D, cudaStream_t st) {
-  if (G < 0 || G > GSB_ADAM_MAX_GROUPS || step < 1) return GSB_E_INVALID;
+  if (G < 0 || G > GSB_ADAM_MAX_GROUPS || (G > 0 && !steps)) return GSB_E_INVALID;
   AdamBatch B;
   B.G = G;
   long long blocks = 0;
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
   for (int k = 0; k < G; ++k) {
     if (n[k] < 0 || (n[k] > 0 && (!p[k] || !g[k] || !m[k] || !v[k]))) return GSB_E_INVALID;
     B.p[k] = p[k]; B.g[k] = g[k]; B.m[k] = m[k]; B.v[k] = v[k]; B.n[k] = n[k];
     B.first_block[k] = blocks;
     blocks += (n[k] + ADAM_PER_BLOCK - 1) / ADAM_PER_BLOCK;
+    if (steps[k] < 1) return GSB_E_INVALID;
+    const double bc1 = 1.0 - pow(beta1, (double)steps[k]);
+    const double bc2 = 1.0 - pow(beta2, (double)steps[k]);
     B.step_size[k] = (float)((double)lr[k] / bc1);
+    B.bc2_sqrt[k] = (float)sqrt(bc2);
   }
   for (int k = G; k <= GSB_ADAM_MAX_GROUPS; ++k) B.first_block[k] = blocks;
   B.omb1 = (float)(1.0 - beta1); B.omb2 = (float)(1.0 - beta2);
-  B.beta1 = (float)beta1; B.beta2 = (float)beta2; B.eps = (float)eps; B.bc2_sqrt = (float)sqrt(bc2); B.grad_scale = grad_scale;
+  B.beta1 = (float)beta1; B.beta2 = (float)beta2; B.eps = (float)eps; B.grad_scale = grad_scale;
   B.stats_n = stats_n;
   B.viewspace_grad = viewspace_grad; B.radii = radii; B.xyz_gradient_accum = xyz_gradient_accum;
   B.denom = denom; B.max_radii2D = max_radii2D;

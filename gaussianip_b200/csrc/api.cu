@@ -153,15 +153,28 @@ int gsb_profile_read(float* ms_out, int* calls_out) {
 
 long long gsb_launch_count(void) { return g_launches.load(); }
 
+int gsb_adam_step_groups(int n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, const long long* counts, const float* lrs, double beta1,
+                         double beta2, double eps, const long long* steps, float grad_scale, long long stats_n,
+                         const float* viewspace_grad, const int32_t* radii, float* xyz_gradient_accum, float* denom,
+                         float* max_radii2D, void* stream) {
+  if (n_groups > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !counts || !lrs || !steps)) return GSB_E_INVALID;
+  return launch_adam_stats(n_groups, params, grads, exp_avg, exp_avg_sq, counts, lrs, beta1, beta2, eps, steps,
+                           grad_scale, stats_n, viewspace_grad, radii, xyz_gradient_accum, denom, max_radii2D,
+                           (cudaStream_t)stream);
+}
+
 int gsb_adam_step(int n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const long long* counts, const float* lrs, double beta1, double beta2,
                   double eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
                   const int32_t* radii, float* xyz_gradient_accum, float* denom, float* max_radii2D,
                   void* stream) {
-  if (n_groups > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !counts || !lrs)) return GSB_E_INVALID;
-  return launch_adam_stats(n_groups, params, grads, exp_avg, exp_avg_sq, counts, lrs, beta1, beta2, eps, step,
-                           grad_scale, stats_n, viewspace_grad, radii, xyz_gradient_accum, denom, max_radii2D,
-                           (cudaStream_t)stream);
+  if (n_groups < 0 || n_groups > GSB_ADAM_MAX_GROUPS || step < 1) return GSB_E_INVALID;
+  long long steps[GSB_ADAM_MAX_GROUPS];
+  for (int k = 0; k < GSB_ADAM_MAX_GROUPS; ++k) steps[k] = step;
+  return gsb_adam_step_groups(n_groups, params, grads, exp_avg, exp_avg_sq, counts, lrs, beta1, beta2, eps, steps,
+                              grad_scale, stats_n, viewspace_grad, radii, xyz_gradient_accum, denom, max_radii2D,
+                              stream);
 }
 
 int gsb_set_blend_variant(int variant) {

@@ -177,8 +177,8 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
                           cudaStream_t st);
 
 int launch_adam_stats(int G, float* const* p, const float* const* g, float* const* m, float* const* v,
-                      const long long* n, const float* lr, double beta1, double beta2, double eps, long long step,
-                      float grad_scale, long long stats_n, const float* viewspace_grad, const int32_t* radii,
+                      const long long* n, const float* lr, double beta1, double beta2, double eps,
+                      const long long* steps, float grad_scale, long long stats_n, const float* viewspace_grad, const int32_t* radii,
                       float* xyz_gradient_accum, float* denom, float* max_radii2D, cudaStream_t st);
 
 // radix sort (binning.cu)

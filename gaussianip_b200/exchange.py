@@ -147,12 +147,14 @@ class GradExchange:
     def end(self) -> None:
         """All ranks' kernels (and therefore all their reds) are complete; owner_push then redistributes."""
         self.hdl.barrier(channel=1)
-        if self.mode == 3 and self.segments:
+        if self.mode == 3:
+            # every rank takes part in the closing barrier, also one that owns no rows (P <= 32 (world - 1)):
+            # gsb_exchange_gather with zero segments launches nothing
             import ctypes as C
             from . import _lib
             n = len(self.segments)
-            off = (C.c_longlong * n)(*[o + self.cur * self.half for o, _ in self.segments])
-            cnt = (C.c_longlong * n)(*[c for _, c in self.segments])
+            off = (C.c_longlong * max(n, 1))(*[o + self.cur * self.half for o, _ in self.segments])
+            cnt = (C.c_longlong * max(n, 1))(*[c for _, c in self.segments])
             dev = self.buf.device
             with torch.cuda.device(dev):
                 _lib.check(_lib.load().gsb_exchange_gather(self.buf.data_ptr(), int(self.hdl.multicast_ptr), n, off, cnt,

@@ -44,7 +44,6 @@ class FusedGaussianAdam:
             raise ValueError("at most 8 parameter groups")
         self.defaults = {"lr": lr, "betas": betas, "eps": eps}
         self.state = defaultdict(dict)
-        self._steps = 0
 
     # ---- torch.optim.Optimizer surface -----------------------------------------------------
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -56,17 +55,47 @@ class FusedGaussianAdam:
                 else:
                     p.grad.zero_()
 
+    # Keys torch.optim.Adam keeps in every param group: emitted so that a state_dict saved here loads into the
+    # reference's torch.optim.Adam (GaussianModel.capture()/restore(), gaussian_model.py:62-82) and vice versa.
+    _TORCH_GROUP_DEFAULTS = {"weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None,
+                             "capturable": False, "differentiable": False, "fused": None,
+                             "decoupled_weight_decay": False}
+
     def state_dict(self) -> dict:
-        return {"steps": self._steps,
-                "groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
-                "state": [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.state[g["params"][0]].items()}
-                          for g in self.param_groups]}
+        """torch.optim.Optimizer.state_dict() layout: ``state`` keyed by parameter index with step / exp_avg /
+        exp_avg_sq, ``param_groups`` with ``params`` as index lists."""
+        state, groups = {}, []
+        for i, g in enumerate(self.param_groups):
+            meta = dict(self._TORCH_GROUP_DEFAULTS)
+            meta.update({k: v for k, v in g.items() if k != "params"})
+            meta["params"] = [i]
+            groups.append(meta)
+            st = self.state.get(g["params"][0])
+            if st and "exp_avg" in st:
+                state[i] = {"step": torch.tensor(float(st.get("step", 0))), "exp_avg": st["exp_avg"].clone(),
+                            "exp_avg_sq": st["exp_avg_sq"].clone()}
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd: dict) -> None:
-        self._steps = int(sd["steps"])
-        for g, meta, st in zip(self.param_groups, sd["groups"], sd["state"]):
-            g.update(meta)
-            self.state[g["params"][0]] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        """Accepts what torch.optim.Adam.state_dict() (or this class) produced for the same groups."""
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        for g, meta in zip(self.param_groups, groups):
+            idx = list(meta["params"])
+            if len(idx) != 1:
+                raise ValueError("each group must hold exactly one tensor")
+            g.update({k: v for k, v in meta.items() if k != "params"})
+            p = g["params"][0]
+            st = sd["state"].get(idx[0], sd["state"].get(str(idx[0])))
+            if st is None:
+                self.state.pop(p, None)
+                continue
+            step = st.get("step", 0)
+            step = int(step.item()) if torch.is_tensor(step) else int(step)
+            self.state[p] = {"step": step,
+                             "exp_avg": st["exp_avg"].detach().to(device=p.device, dtype=p.dtype).clone(),
+                             "exp_avg_sq": st["exp_avg_sq"].detach().to(device=p.device, dtype=p.dtype).clone()}
 
     def _state_of(self, p: torch.Tensor) -> dict:
         st = self.state[p]
@@ -85,7 +114,6 @@ class FusedGaussianAdam:
         dev = (active[0]["params"][0] if active else densify[0]).device
         if dev.type != "cuda":
             raise ValueError("FusedGaussianAdam runs on CUDA tensors only (no CPU fallback)")
-        self._steps += 1
         n = len(active)
         ptr = lambda ts: (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in ts])
         ps, gs, ms, vs, keep = [], [], [], [], []
@@ -105,8 +133,8 @@ class FusedGaussianAdam:
             ps.append(p); gs.append(grad); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
         b1, b2 = (active[0].get("betas", self.defaults["betas"]) if active else self.defaults["betas"])
         eps = active[0].get("eps", self.defaults["eps"]) if active else self.defaults["eps"]
-        # one bias-correction step count per launch, as in torch when all groups step together
-        step = max((self.state[g["params"][0]]["step"] for g in active), default=self._steps)
+        # bias correction per group from ITS step count (a group whose grad was None on earlier steps lags, as in torch)
+        steps = (C.c_longlong * max(n, 1))(*[int(self.state[g["params"][0]]["step"]) for g in active])
         counts = (C.c_longlong * max(n, 1))(*[p.numel() for p in ps])
         lrs = (C.c_float * max(n, 1))(*[float(g["lr"]) for g in active])
         stats_n, sp = 0, [None] * 5
@@ -122,8 +150,8 @@ class FusedGaussianAdam:
                     raise ValueError("densification statistics must be contiguous fp32 with one entry per Gaussian")
             sp = [vgrad.data_ptr(), radii.data_ptr(), acc.data_ptr(), den.data_ptr(), mr.data_ptr()]
         with torch.cuda.device(dev):
-            rc = lib.gsb_adam_step(n, ptr(ps), ptr(gs), ptr(ms), ptr(vs), counts, lrs, float(b1), float(b2), float(eps),
-                                   int(step), float(grad_scale), int(stats_n), sp[0], sp[1], sp[2], sp[3], sp[4],
+            rc = lib.gsb_adam_step_groups(n, ptr(ps), ptr(gs), ptr(ms), ptr(vs), counts, lrs, float(b1), float(b2),
+                                          float(eps), steps, float(grad_scale), int(stats_n), sp[0], sp[1], sp[2], sp[3], sp[4],
                                    torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(rc, "gsb_adam_step")
+        _lib.check(rc, "gsb_adam_step_groups")
         del keep

@@ -535,7 +535,6 @@ class _RasterizeGaussians(torch.autograd.Function):
                              colors if has_col else None, opacities, scales if has_sc else None,
                              rotations if has_rot else None, cov3D if has_cov else None, radii,
                              grad_color, grad_depth, grad_alpha)
-        ctx.sv = None
         return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
                 out["rotations"], out["cov3D"], None)
 
@@ -616,7 +615,6 @@ class _RasterizeViews(torch.autograd.Function):
                                   colors if has_col else None, opacities, scales if has_sc else None,
                                   rotations if has_rot else None, cov3D if has_cov else None, radii,
                                   grad_color, grad_depth, grad_alpha, exchange=ctx.exchange, raw=ctx.raw)
-            ctx.svs = None
             return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
                     out["rotations"], out["cov3D"], None, None, None)
         out = None
@@ -628,7 +626,6 @@ class _RasterizeViews(torch.autograd.Function):
                                  None if grad_depth is None else grad_depth[v],
                                  None if grad_alpha is None else grad_alpha[v], out=out, accumulate=v > 0,
                                  raw=ctx.raw)
-        ctx.svs = None
         return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
                 out["rotations"], out["cov3D"], None, None, None)
 

@@ -146,22 +146,26 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
             "radii": radii, "radii_per_view": radii_v, "depth_3dgs": depth, "alpha_3dgs": alpha}
 
 
-def render_deformed(viewpoint_camera, means3D, feats, opacity, scales, rotations, active_sh_degree, pipe,
-                    bg_color: torch.Tensor, scaling_modifier=1.0):
-    screenspace_points = torch.zeros_like(means3D, requires_grad=True) + 0
+def render_deformed(viewpoint_camera, feats, means3D, opacity, scales, rotations, active_sh_degree, pipe,
+                    bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+    """gaussian_renderer/__init__.py:195-265, same positional order (the callers pass ``(cam, feats, means3D, ...)``
+    positionally: GaussianIP_anim.py:511, avatar/__init__.py:377).  ``feats`` [P,3] are precomputed colours,
+    [P,K,3] spherical harmonics; the dictionary has no depth / alpha entries; ``override_color`` is accepted and
+    ignored exactly as the reference does."""
+    screenspace_points = torch.zeros_like(means3D, dtype=torch.float32, requires_grad=True) + 0
     try:
         screenspace_points.retain_grad()
     except Exception:
         pass
     rasterizer = GaussianRasterizer(_settings(viewpoint_camera, bg_color, scaling_modifier, active_sh_degree))
     shs = colors_precomp = None
-    if feats.ndim == 2:
+    if len(feats.shape) == 2:
         colors_precomp = feats
     else:
         shs = feats
     rendered_image, radii, _depth, _alpha = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp, opacities=opacity,
-        scales=scales, rotations=rotations, cov3D_precomp=None)
+        scales=scales, rotations=rotations)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii}
 
@@ -169,7 +173,10 @@ def render_deformed(viewpoint_camera, means3D, feats, opacity, scales, rotations
 class Renderer:
     """gs_renderer.Renderer.render (gs_renderer.py:923-1014) over any object with the getters."""
 
-    def __init__(self, gaussians, sh_degree=3, white_background=True, device="cuda"):
+    def __init__(self, sh_degree=3, white_background=True, gaussians=None, device="cuda"):
+        """Positional signature of the reference, ``Renderer(sh_degree, white_background)`` (gs_renderer.py:882).  The
+        reference constructs its own GaussianModel; here the model (anything with the getters) is handed in
+        with ``gaussians=`` or assigned to ``self.gaussians`` afterwards."""
         self.sh_degree = sh_degree
         self.white_background = white_background
         self.gaussians = gaussians

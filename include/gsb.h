@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 2
+#define GSB_ABI_VERSION 3
 
 enum {
   GSB_OK = 0,
@@ -211,6 +211,13 @@ int gsb_adam_step(int n_groups, float* const* params, const float* const* grads,
                   double eps, long long step, float grad_scale, long long stats_n, const float* viewspace_grad,
                   const int32_t* radii, float* xyz_gradient_accum, float* denom, float* max_radii2D,
                   void* stream);
+/* Same launch with one 1-based step count PER GROUP (steps[n_groups], host array): torch.optim.Adam keeps `step`
+ * per parameter, so a group whose gradient was None on earlier steps has its own bias correction. */
+int gsb_adam_step_groups(int n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, const long long* counts, const float* lrs, double beta1,
+                         double beta2, double eps, const long long* steps, float grad_scale, long long stats_n,
+                         const float* viewspace_grad, const int32_t* radii, float* xyz_gradient_accum,
+                         float* denom, float* max_radii2D, void* stream);
 
 /* replaces `simple_knn._C.distCUDA2` (simple-knn/spatial.cu:15-26 -> SimpleKNN::knn,
  * simple_knn.cu:186-221; callers gaussian_model.py:123, gs_renderer.py:387): mean_dist2[i] = mean of the

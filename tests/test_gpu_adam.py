@@ -89,3 +89,62 @@ def test_amp_unscale_and_state_roundtrip(cuda_device):
     cpu_p.grad = torch.zeros(3)
     with pytest.raises(ValueError, match="CUDA"):        # no CPU fallback
         FusedGaussianAdam([{"params": [cpu_p], "lr": 1e-3, "name": "cpu"}]).step()
+
+
+def test_state_dict_interchanges_with_torch_adam(cuda_device):
+    """GaussianModel.capture()/restore() round-trip optimizer.state_dict() (gaussian_model.py:62-82): a checkpoint
+    written by the reference's torch.optim.Adam loads here and continues identically, and the reverse."""
+    from gaussianip_b200.optim import FusedGaussianAdam
+    P, dev = 777, cuda_device
+    ref_groups, our_groups = _groups(P, dev, seed=3), _groups(P, dev, seed=3)
+    ref = torch.optim.Adam(ref_groups, lr=0.0, eps=1e-15)
+    ours = FusedGaussianAdam(our_groups, lr=0.0, eps=1e-15)
+    g = torch.Generator().manual_seed(5)
+
+    def grads():
+        for rg, og in zip(ref_groups, our_groups):
+            gr = torch.randn(rg["params"][0].shape, generator=g).to(dev)
+            rg["params"][0].grad, og["params"][0].grad = gr.clone(), gr.clone()
+
+    for _ in range(3):
+        grads(); ref.step(); ours.step()
+    sd_t, sd_o = ref.state_dict(), ours.state_dict()
+    assert set(sd_o) == {"state", "param_groups"} and set(sd_o["state"]) == set(sd_t["state"])
+    for i in sd_t["state"]:
+        assert set(sd_t["state"][i]) <= set(sd_o["state"][i])
+        assert float(sd_o["state"][i]["step"]) == float(sd_t["state"][i]["step"]) == 3.0
+    assert [pg["params"] for pg in sd_o["param_groups"]] == [pg["params"] for pg in sd_t["param_groups"]]
+    assert [pg["name"] for pg in sd_o["param_groups"]] == list(LRS)
+    # cross-load: torch checkpoint -> fused, fused checkpoint -> torch, then two more steps each
+    ref2 = torch.optim.Adam(ref_groups, lr=0.0, eps=1e-15)
+    ours2 = FusedGaussianAdam(our_groups, lr=0.0, eps=1e-15)
+    ref2.load_state_dict(sd_o)
+    ours2.load_state_dict(sd_t)
+    for _ in range(2):
+        grads(); ref2.step(); ours2.step()
+    for rg, og in zip(ref_groups, our_groups):
+        torch.testing.assert_close(og["params"][0], rg["params"][0], rtol=2e-6, atol=1e-7)
+        assert int(ours2.state[og["params"][0]]["step"]) == 5
+
+
+def test_group_without_gradient_keeps_its_own_step_count(cuda_device):
+    """torch.optim.Adam keeps `step` per parameter: a group whose .grad was None for two steps is bias-corrected
+    with ITS count when it joins."""
+    from gaussianip_b200.optim import FusedGaussianAdam
+    P, dev = 1030, cuda_device
+    ref_groups, our_groups = _groups(P, dev, seed=8), _groups(P, dev, seed=8)
+    ref = torch.optim.Adam(ref_groups, lr=0.0, eps=1e-15)
+    ours = FusedGaussianAdam(our_groups, lr=0.0, eps=1e-15)
+    g = torch.Generator().manual_seed(9)
+    for it in range(5):
+        for k, (rg, og) in enumerate(zip(ref_groups, our_groups)):
+            if k == 2 and it < 2:                       # f_rest: no gradient on the first two steps
+                rg["params"][0].grad = og["params"][0].grad = None
+                continue
+            gr = torch.randn(rg["params"][0].shape, generator=g).to(dev)
+            rg["params"][0].grad, og["params"][0].grad = gr.clone(), gr.clone()
+        ref.step(); ours.step()
+    for rg, og in zip(ref_groups, our_groups):
+        torch.testing.assert_close(og["params"][0], rg["params"][0], rtol=2e-6, atol=1e-7)
+    assert int(ours.state[our_groups[2]["params"][0]]["step"]) == 3
+    assert int(ours.state[our_groups[0]["params"][0]]["step"]) == 5

@@ -108,7 +108,7 @@ def test_config4_playback_forward_only(cuda_device):
     with torch.no_grad():
         for i, cam in enumerate(cams):
             xyz = synthetic.playback_sway(cl.xyz, i * 17, 136)
-            r = renderer.Renderer(Model(cl, xyz), sh_degree=0, white_background=False, device=dev)
+            r = renderer.Renderer(0, False, gaussians=Model(cl, xyz), device=dev)
             out = r.render(cam)
             assert set(out) == {"image", "depth", "alpha", "viewspace_points", "visibility_filter", "radii"}
             img = out["image"]

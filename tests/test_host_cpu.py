@@ -64,7 +64,10 @@ def test_ctypes_prototypes_match_the_header():
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.gsb_abi_version() == 2
+    from gaussianip_b200 import _lib
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gsb.h")).read()
+    assert lib.gsb_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define GSB_ABI_VERSION (\d+)", hdr).group(1))
     assert lib.gsb_strerror(0) == b"ok"
     assert b"invalid" in lib.gsb_strerror(-1)
 
