@@ -21,7 +21,7 @@ class GsbSettings(C.Structure):
                 ("sh_degree", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
                 ("raw_inputs", C.c_int32),
                 ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
-                ("campos", C.c_void_p)]
+                ("campos", C.c_void_p), ("tanfov_dev", C.c_void_p)]
 
 
 _LAYOUT_FIELDS = ["saved_bytes", "off_geom", "off_clamped", "off_counts", "off_point_list", "off_ranges",

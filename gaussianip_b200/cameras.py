@@ -85,14 +85,12 @@ class Camera:
         return math.tan(self.FoVy * 0.5)
 
 
-def cameras_from_c2w(c2ws, fovys, height, width, device="cuda"):
-    """Build the Camera objects of one step with ONE pinned staging buffer and ONE asynchronous
-    host->device copy (the reference builds each camera separately with two GPU inversions,
-    threestudio/systems/GaussianIP.py:155; a pageable per-tensor upload would also block the host
-    until the stream drains).  Values are identical to Camera(c2w, fovy, height, width)."""
+def _camera_rows(c2ws, fovys, height, width):
+    """Host algebra for n cameras at once (one LAPACK call for all inversions): rows of 53 floats
+    [world_view 16 | projection 16 | full_proj 16 | centre 3 | tanfovx, tanfovy] with values identical to
+    Camera(c2w, fovy, height, width); also returns (FoVx, FoVy) per camera."""
     n = len(c2ws)
     fovys = [float(f) for f in fovys]
-    # batched host algebra (one LAPACK call for all inversions); values identical to the per-camera code
     c2w = np.stack([np.asarray(c.detach().cpu() if torch.is_tensor(c) else c, dtype=np.float64) for c in c2ws])
     w2c = np.linalg.inv(c2w)
     w2c[:, 1:3, :3] *= -1.0
@@ -102,10 +100,24 @@ def cameras_from_c2w(c2ws, fovys, height, width, device="cuda"):
     proj = np.stack([projection_matrix(0.01, 100.0, fx, fy).T for fx, fy in zip(fovxs, fovys)])
     full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
     center = np.linalg.inv(view)[:, 3, :3]
-    rows = np.concatenate((view.reshape(n, 16), proj.reshape(n, 16), full.reshape(n, 16), center), axis=1)
-    stage = torch.from_numpy(rows.astype(np.float32))
-    if torch.device(device).type == "cuda":
-        stage = stage.pin_memory()
+    tanfov = np.array([[math.tan(fx * 0.5), math.tan(fy * 0.5)] for fx, fy in zip(fovxs, fovys)])
+    rows = np.concatenate((view.reshape(n, 16), proj.reshape(n, 16), full.reshape(n, 16), center, tanfov), axis=1)
+    return rows.astype(np.float32), fovxs, fovys
+
+
+ROW_FLOATS = 53
+
+
+def _bind_rows(cams, dev_buf):
+    for i, cam in enumerate(cams):
+        cam.world_view_transform = dev_buf[i, 0:16].view(4, 4)
+        cam.projection_matrix = dev_buf[i, 16:32].view(4, 4)
+        cam.full_proj_transform = dev_buf[i, 32:48].view(4, 4)
+        cam.camera_center = dev_buf[i, 48:51]
+        cam.tanfov_dev = dev_buf[i, 51:53]     # device copy of (tanfovx, tanfovy), see rasterize_views(tanfov_dev=)
+
+
+def _blank_cameras(fovxs, fovys, height, width, device):
     cams = []
     for fovx, fovy in zip(fovxs, fovys):
         cam = Camera.__new__(Camera)
@@ -114,14 +126,60 @@ def cameras_from_c2w(c2ws, fovys, height, width, device="cuda"):
         cam.zfar, cam.znear, cam.trans, cam.scale = 100.0, 0.01, torch.zeros(3), 1.0
         cam.data_device = torch.device(device)
         cams.append(cam)
+    return cams
+
+
+def cameras_from_c2w(c2ws, fovys, height, width, device="cuda"):
+    """Build the Camera objects of one step with ONE pinned staging buffer and ONE asynchronous
+    host->device copy (the reference builds each camera separately with two GPU inversions,
+    threestudio/systems/GaussianIP.py:155; a pageable per-tensor upload would also block the host
+    until the stream drains).  Values are identical to Camera(c2w, fovy, height, width)."""
+    rows, fovxs, fovys = _camera_rows(c2ws, fovys, height, width)
+    stage = torch.from_numpy(rows)
+    if torch.device(device).type == "cuda":
+        stage = stage.pin_memory()
+    cams = _blank_cameras(fovxs, fovys, height, width, device)
     dev_buf = stage.to(device, non_blocking=True)
-    for i, cam in enumerate(cams):
-        cam.world_view_transform = dev_buf[i, 0:16].view(4, 4)
-        cam.projection_matrix = dev_buf[i, 16:32].view(4, 4)
-        cam.full_proj_transform = dev_buf[i, 32:48].view(4, 4)
-        cam.camera_center = dev_buf[i, 48:51]
+    _bind_rows(cams, dev_buf)
+    for cam in cams:
         cam._stage = stage            # keep the pinned buffer alive until the copy has run
     return cams
+
+
+class CameraBlock:
+    """n cameras whose matrices live at FIXED device addresses (one [n, 53] tensor), refreshed per step with one
+    asynchronous copy from a ring of pinned staging buffers.  A step captured in a CUDA graph
+    (gaussianip_b200.graph.CapturedStep) reads its cameras from here, so replaying it with new cameras is
+    ``block.update(c2ws, fovys)`` followed by the replay; the intrinsics travel in the same rows
+    (``cam.tanfov_dev``) because kernel arguments passed by value are frozen at capture time."""
+
+    def __init__(self, n: int, height: int, width: int, device="cuda", ring: int = 4):
+        self.n, self.height, self.width = int(n), int(height), int(width)
+        self.device = torch.device(device)
+        self.dev = torch.zeros(self.n, ROW_FLOATS, dtype=torch.float32, device=self.device)
+        self.stage = [torch.zeros(self.n, ROW_FLOATS, dtype=torch.float32) for _ in range(ring)]
+        if self.device.type == "cuda":
+            self.stage = [t.pin_memory() for t in self.stage]
+        self.slot = 0
+        self.cameras = _blank_cameras([1.0] * self.n, [1.0] * self.n, height, width, self.device)
+        _bind_rows(self.cameras, self.dev)
+
+    def update(self, c2ws, fovys):
+        """Host algebra + ONE async H2D on the current stream.  The host may run at most ``ring - 1`` updates
+        ahead of the device (the caller's per-step validation / loss read-back bounds that)."""
+        if len(c2ws) != self.n:
+            raise ValueError(f"expected {self.n} cameras")
+        rows, fovxs, fovys = _camera_rows(c2ws, fovys, self.height, self.width)
+        st = self.stage[self.slot]
+        self.slot = (self.slot + 1) % len(self.stage)
+        st.copy_(torch.from_numpy(rows))
+        self.dev.copy_(st, non_blocking=True)
+        for cam, fx, fy in zip(self.cameras, fovxs, fovys):
+            cam.FoVx, cam.FoVy = fx, fy
+        return self.cameras
+
+    def nbytes(self) -> int:
+        return self.n * ROW_FLOATS * 4
 
 
 class MiniCam:

@@ -45,6 +45,7 @@ struct View {           // settings with device pointers, passed by value to ker
   const float* view;
   const float* proj;
   const float* campos;
+  const float* tanfov_dev;   // optional device [2] = {tanfovx, tanfovy}: overrides the by-value intrinsics (see GsbSettings)
 };
 
 inline View make_view(const GsbSettings* s) {
@@ -56,7 +57,21 @@ inline View make_view(const GsbSettings* s) {
   v.focal_y = (float)v.H / (2.0f * s->tanfovy);
   v.scale_mod = s->scale_modifier; v.sh_degree = s->sh_degree; v.raw = s->raw_inputs;
   v.bg = s->bg; v.view = s->viewmatrix; v.proj = s->projmatrix; v.campos = s->campos;
+  v.tanfov_dev = s->tanfov_dev;
   return v;
+}
+
+// Intrinsics of a view: k[0..3] = tanfovx, tanfovy, focal_x, focal_y.  With GsbSettings.tanfov_dev they are read from
+// device memory (a captured CUDA graph can then be replayed with new cameras) and the focal lengths are formed
+// with the same fp32 operations make_view uses on the host.
+__device__ __forceinline__ void load_intrinsics(const View& v, float* k) {
+  float tx = v.tanfovx, ty = v.tanfovy, fx = v.focal_x, fy = v.focal_y;
+  if (v.tanfov_dev) {
+    tx = v.tanfov_dev[0]; ty = v.tanfov_dev[1];
+    fx = __fdiv_rn((float)v.W, __fmul_rn(2.0f, tx));
+    fy = __fdiv_rn((float)v.H, __fmul_rn(2.0f, ty));
+  }
+  k[0] = tx; k[1] = ty; k[2] = fx; k[3] = fy;
 }
 
 // The Geom record stores the conic PRE-SCALED for the blend kernels: with qa = -0.5 log2(e) A, qb = -log2(e) B,

@@ -48,7 +48,7 @@ __device__ __forceinline__ float sh_channel(int deg, const float* __restrict__ s
 }
 
 __device__ __forceinline__ void
-preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, const float* sCam,
+preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, const float* sCam, const float* sK,
                const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rots,
                const float* __restrict__ opac, const float* __restrict__ shs, const float* __restrict__ colors,
                const float* __restrict__ cov3Dp, int32_t* __restrict__ radii, Geom* __restrict__ geom,
@@ -95,13 +95,13 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
     }
 
     // EWA projection
-    const float limx = 1.3f * v.tanfovx, limy = 1.3f * v.tanfovy;
+    const float limx = 1.3f * sK[0], limy = 1.3f * sK[1];
     const float txtz = tx / tz, tytz = ty / tz;
     const float txc = fminf(limx, fmaxf(-limx, txtz)) * tz;
     const float tyc = fminf(limy, fmaxf(-limy, tytz)) * tz;
     const float tz2 = tz * tz;
-    const float J00 = v.focal_x / tz, J02 = -(v.focal_x * txc) / tz2;
-    const float J11 = v.focal_y / tz, J12 = -(v.focal_y * tyc) / tz2;
+    const float J00 = sK[2] / tz, J02 = -(sK[2] * txc) / tz2;
+    const float J11 = sK[3] / tz, J12 = -(sK[3] * tyc) / tz2;
     // W(i,j) = sV[i + 4j]
     const float T00 = J00 * sV[0] + J02 * sV[2], T01 = J00 * sV[4] + J02 * sV[6],
                 T02 = J00 * sV[8] + J02 * sV[10];
@@ -194,18 +194,19 @@ preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
                       uint8_t* __restrict__ clamped, ushort4* __restrict__ rect,
                       uint32_t* __restrict__ tiles, uint32_t* __restrict__ dkeys,
                       uint32_t* __restrict__ ghist0) {
-  __shared__ float sV[16], sM[16], sCam[3];
+  __shared__ float sV[16], sM[16], sCam[3], sK[4];   // sK: tanfovx, tanfovy, focal_x, focal_y
   __shared__ uint32_t s_h0[256];   // digit-0 histogram of the depth keys (first pass of the depth sort)
   s_h0[threadIdx.x] = 0;
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sM[threadIdx.x] = v.proj[threadIdx.x]; }
   if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  if (threadIdx.x == 32) load_intrinsics(v, sK);
   __syncthreads();
   // PRE_IPT Gaussians per thread: 4x fewer CTAs flushing their 256-bin histogram to the same
   // 256 global counters (one flush per 256 Gaussians cost +22 us of same-address L2 atomics)
 #pragma unroll 1
   for (int k = 0; k < PRE_IPT; ++k) {
     const int i = (blockIdx.x * PRE_IPT + k) * 256 + threadIdx.x;
-    if (i < P) preprocess_one(v, i, K, sV, sM, sCam, means3D, scales, rots, opac, shs, colors, cov3Dp, radii, geom,
+    if (i < P) preprocess_one(v, i, K, sV, sM, sCam, sK, means3D, scales, rots, opac, shs, colors, cov3Dp, radii, geom,
                               clamped, rect, tiles, dkeys, s_h0);
   }
   __syncthreads();

@@ -75,7 +75,7 @@ struct Accum {            // per-Gaussian gradient sums over the views of one la
 // SH gradient sums stay in registers); sh = this Gaussian's coefficient row (staged in shared memory).
 template <int DEG>
 __device__ __forceinline__ void
-view_contrib(const View& v, int i, const float* sV, const float* sM, const float* sCam,
+view_contrib(const View& v, int i, const float* sV, const float* sM, const float* sCam, const float* sK,
              const float* __restrict__ means3D, const float (&sc_act)[3], const float4 q_act,
              const float* sh, const float* __restrict__ cov3Dp, const Geom* __restrict__ geom,
              const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, bool precomp_color,
@@ -198,7 +198,7 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
   }
 
   // ---- EWA projection (recomputed) and its backward ------------------------------------------
-  const float limx = 1.3f * v.tanfovx, limy = 1.3f * v.tanfovy;
+  const float limx = 1.3f * sK[0], limy = 1.3f * sK[1];
   const float tz_inv = 1.0f / tz;
   const float txtz = tx * tz_inv, tytz = ty * tz_inv;
   const float x_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
@@ -206,7 +206,7 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
   const float txc = fminf(limx, fmaxf(-limx, txtz)) * tz;
   const float tyc = fminf(limy, fmaxf(-limy, tytz)) * tz;
   const float tz2 = tz_inv * tz_inv, tz3 = tz2 * tz_inv;
-  const float fx = v.focal_x, fy = v.focal_y;
+  const float fx = sK[2], fy = sK[3];
   const float J00 = fx * tz_inv, J02 = -fx * txc * tz2, J11 = fy * tz_inv, J12 = -fy * tyc * tz2;
   float T0[3], T1[3];
 #pragma unroll
@@ -309,12 +309,13 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   constexpr int NC3 = 3 * (DEG + 1) * (DEG + 1);
   constexpr bool MC = MODE != 0;
   constexpr bool MM = MODE == 2;
-  __shared__ float sV[GSB_MAX_VIEWS][16], sM[GSB_MAX_VIEWS][16], sCam[GSB_MAX_VIEWS][4];
+  __shared__ float sV[GSB_MAX_VIEWS][16], sM[GSB_MAX_VIEWS][16], sCam[GSB_MAX_VIEWS][4], sK[GSB_MAX_VIEWS][4];
   for (int t = threadIdx.x; t < B.V * 16; t += blockDim.x) {
     sV[t >> 4][t & 15] = B.a[t >> 4].v.view[t & 15];
     sM[t >> 4][t & 15] = B.a[t >> 4].v.proj[t & 15];
   }
   for (int t = threadIdx.x; t < B.V * 3; t += blockDim.x) sCam[t / 3][t % 3] = B.a[t / 3].v.campos[t % 3];
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + B.V) load_intrinsics(B.a[threadIdx.x - 128].v, sK[threadIdx.x - 128]);
   __syncthreads();
   const int i = blockIdx.x * 256 + threadIdx.x;
   // a Gaussian's coefficient row is K*12 contiguous bytes; the rows of a warp are contiguous too, so
@@ -346,7 +347,7 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
     for (int vi = 0; vi < B.V; ++vi) {
       const BwdView& bv = B.a[vi];
       if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
-      view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], means3D, sc, q, my_sh, cov3Dp, bv.geom, bv.clamped,
+      view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], sK[vi], means3D, sc, q, my_sh, cov3Dp, bv.geom, bv.clamped,
                         bv.ggrad, dcolors != nullptr, A);
       o_act = reinterpret_cast<const float4*>(bv.geom + i)[1].w;      // activated opacity, as the forward stored it
     }

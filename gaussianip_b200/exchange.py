@@ -92,6 +92,10 @@ class GradExchange:
         self.hdl = None
         self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         self.steps = 0
+        # static = True: graph-safe protocol.  A captured step always runs the same instructions, so the halves
+        # cannot alternate: half 0 is used every time, zeroed in-stream at the start of the backward, with one more
+        # barrier so that nobody adds into a copy that is still being zeroed.
+        self.static = False
 
     @staticmethod
     def available(device: torch.device, group=None) -> bool:
@@ -140,6 +144,11 @@ class GradExchange:
     def begin(self) -> None:
         """Pick this step's half (already zero on every rank) and zero the other one for the next step; the
         zeroing is ordered before this step's closing barrier, so nobody can add into it too early."""
+        if self.static:
+            self.cur = 0
+            self.buf[:self.half].zero_()
+            self.hdl.barrier(channel=0)
+            return
         self.cur = self.steps & 1
         other = 1 - self.cur
         self.buf[other * self.half:(other + 1) * self.half].zero_()
@@ -162,6 +171,15 @@ class GradExchange:
                            "gsb_exchange_gather")
             self.hdl.barrier(channel=2)
         self.steps += 1
+
+    def reset(self) -> None:
+        """COLLECTIVE: zero both halves everywhere (after switching `static`, or to resynchronise the alternation)."""
+        if self.buf is None:
+            return
+        self.hdl.barrier(channel=0)
+        self.buf.zero_()
+        self.hdl.barrier(channel=0)
+        self.steps = 0
 
     def output_ptr(self, name: str) -> Optional[int]:
         """What the kernel is given for this field: the multicast address (push_all) or the local copy (owner_push)."""

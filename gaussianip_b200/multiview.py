@@ -157,6 +157,9 @@ class ViewParallel:
         step's results are discarded and the step is run again with the raised capacity.  Local only —
         there is no collective inside, so ranks need not agree on the number of attempts."""
         from . import rasterizer
+        if rasterizer._active_speculation() is not None:
+            # the caller owns the step (e.g. graph.CapturedStep captures / replays it and validates the counts)
+            return body()
         for _ in range(8):
             with rasterizer.speculation() as spec:
                 result = body()
@@ -239,4 +242,7 @@ class ViewParallel:
             vg = vg if vg is not None else torch.zeros_like(b.viewspace_points)
         else:
             vg = b.viewspace_grad()
-        return {"loss": total, "radii": radii, "viewspace_grad": vg, "local_views": local}
+        # "grads": the tensors that hold this step's parameter gradients (what .grad points at right now); a caller
+        # that replays the step from a CUDA graph reads them from here, because .grad follows the LAST capture
+        return {"loss": total, "radii": radii, "viewspace_grad": vg, "local_views": local,
+                "grads": {k: p.grad for k, p in b.params.items()}}

@@ -120,7 +120,7 @@ def _small(t: torch.Tensor, n: int, name: str, device) -> torch.Tensor:
     return t
 
 
-def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0):
+def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0, tanfov_dev: Optional[torch.Tensor] = None):
     bg = _small(rs.bg, 3, "bg", device)
     view = _small(rs.viewmatrix, 16, "viewmatrix", device)
     proj = _small(rs.projmatrix, 16, "projmatrix", device)
@@ -130,8 +130,8 @@ def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0):
     s = _lib.GsbSettings(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
                          float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)),
                          int(bool(rs.debug)), int(raw), bg.data_ptr(), view.data_ptr(), proj.data_ptr(),
-                         campos.data_ptr())
-    return s, (bg, view, proj, campos)      # keep the tensors alive next to the struct
+                         campos.data_ptr(), None if tanfov_dev is None else _small(tanfov_dev, 2, "tanfov_dev", device).data_ptr())
+    return s, (bg, view, proj, campos, tanfov_dev)      # keep the tensors alive next to the struct
 
 
 class _Saved:
@@ -174,8 +174,10 @@ class _ForwardCall:
     the 32-byte counts copy and, if D exceeded the instance capacity, re-enqueues with a larger
     workspace (nothing can have observed the outputs yet)."""
 
-    def __init__(self, rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0):
+    def __init__(self, rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0,
+                 tanfov_dev=None):
         self.raw = raw
+        self.tanfov_dev = tanfov_dev
         self.args = (means3D, shs, colors, opacities, scales, rotations, cov3D)
         device = means3D.device
         if device.type != "cuda":
@@ -187,6 +189,7 @@ class _ForwardCall:
         self.rs = rs
         self.out = out
         self.stream = None
+        self.counts = None
 
     def enqueue(self):
         lib = _lib.load()
@@ -196,7 +199,7 @@ class _ForwardCall:
             if self.stream is None:
                 self.stream = torch.cuda.current_stream(device)
                 self.ws = _workspace(device)
-                self.s, self.keep = _make_settings(self.rs, device, self.raw)
+                self.s, self.keep = _make_settings(self.rs, device, self.raw, self.tanfov_dev)
                 if self.out is not None:
                     self.color, self.radii, self.depth, self.alpha = self.out   # caller-owned contiguous slices
                 else:
@@ -205,8 +208,18 @@ class _ForwardCall:
                     self.alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
                     self.radii = torch.empty(P, dtype=torch.int32, device=device)
             ws = self.ws
-            if ws.pending is not None and ws.pending is not self:
-                ws.pending.settle()         # its counts buffer is about to be reused
+            spec = _active_speculation()
+            if spec is not None and spec.capture:
+                # CUDA-graph capture (gaussianip_b200.graph): the counts copy becomes a graph node writing this
+                # call's OWN pinned block on every replay; no event (a captured event cannot be waited on)
+                if self.counts is None:
+                    self.counts = spec.take_counts()
+                counts_ptr, event = self.counts.data_ptr(), None
+            else:
+                if ws.pending is not None and ws.pending is not self:
+                    ws.pending.settle()         # its counts buffer is about to be reused
+                self.counts = None
+                counts_ptr, event = ws.host_counts.data_ptr(), ws.event.cuda_event
             self.d_cap = ws.capacity_for(P)
             self.L = _lib.layout(P, H, W, self.d_cap)
             self.scratch = ws.ensure_scratch(self.L.scratch_bytes)
@@ -215,7 +228,7 @@ class _ForwardCall:
                                  _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), self.radii.data_ptr(),
                                  self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
                                  self.block.data_ptr(), self.scratch.data_ptr(), self.d_cap, ws.binning_mode,
-                                 ws.host_counts.data_ptr(), ws.event.cuda_event, self.stream.cuda_stream)
+                                 counts_ptr, event, self.stream.cuda_stream)
             _lib.check(rc, "gsb_forward")
         return self
 
@@ -243,7 +256,8 @@ class _ForwardCall:
             # owner of the step validates them after everything is enqueued and redoes the step
             # if this view did not fit
             self.sv = self._saved(None)
-            ws.pending = self
+            if not spec.capture:
+                ws.pending = self
             spec.calls.append(self)
             return self.color, self.radii, self.depth, self.alpha, self.sv
         while True:
@@ -263,6 +277,19 @@ class _ForwardCall:
         Returns False if the view overflowed its instance capacity; the capacity is then raised
         for the next attempt."""
         ws, P = self.ws, self.P
+        if self.counts is not None:
+            # captured call: the caller has waited for the replay (graph.CapturedStep.validate)
+            D = int(self.counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
+            self.fits = D <= self.d_cap
+            if self.fits:
+                self.sv.num_rendered = D
+                _stats["num_rendered"] = D
+                _stats["views"] += 1
+                _stats["num_rendered_sum"] += D
+            else:
+                ws.d_cap = max(ws.d_cap, int(D * 1.25) + 4096)
+                ws.retries += 1
+            return self.fits
         if ws.pending is not self:
             return self.fits
         ws.event.synchronize()
@@ -286,8 +313,21 @@ class speculation:
     again (gaussianip_b200.multiview.ViewParallel does).  Removes the one host stall per step
     that otherwise lets the GPU run dry between the forward and the backward."""
 
-    def __init__(self):
+    def __init__(self, capture: bool = False, counts_pool=None):
+        """capture=True (used by gaussianip_b200.graph.CapturedStep while a CUDA graph is being captured): every
+        forward writes its instance counts to its own block of ``counts_pool`` (pinned int32 [n, 8], allocated
+        BEFORE the capture) and records no event; ``validate(keep=True)`` may then be called after every replay."""
         self.calls = []
+        self.capture = bool(capture)
+        self.counts_pool = counts_pool
+        self.counts_used = 0
+
+    def take_counts(self) -> torch.Tensor:
+        if self.counts_pool is None or self.counts_used >= self.counts_pool.shape[0]:
+            raise RuntimeError("capture needs a pinned counts pool with one row per forward call")
+        row = self.counts_pool[self.counts_used]
+        self.counts_used += 1
+        return row
 
     def __enter__(self):
         if getattr(_tls, "spec", None) is not None:
@@ -299,11 +339,12 @@ class speculation:
         _tls.spec = None
         return False
 
-    def validate(self) -> bool:
+    def validate(self, keep: bool = False) -> bool:
         ok = True
         for call in self.calls:
             ok = call.settle() and ok
-        self.calls = []
+        if not keep:
+            self.calls = []
         return ok
 
 
@@ -314,8 +355,10 @@ def _active_speculation():
     return getattr(_tls, "spec", None)
 
 
-def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0):
-    return _ForwardCall(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out, raw).enqueue().finish()
+def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0,
+                  tanfov_dev=None):
+    return _ForwardCall(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out, raw,
+                        tanfov_dev).enqueue().finish()
 
 
 # Side streams for the batched multi-view entry: the binning stages of a 1-2 M instance view are
@@ -346,23 +389,28 @@ def set_multistream(enabled: bool) -> None:
     _multistream = bool(enabled)
 
 
+MAX_SIDE_STREAMS = 8
+
+
 def _streams_for(device: torch.device, n: int):
+    """One side stream per view, at most MAX_SIDE_STREAMS: with more views (the 64 VCR views of one step) view v
+    shares stream v mod 8 — and with it that stream's scratch workspace — with views v + 8, v + 16, ..."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     pool = _side_streams.setdefault(key, [])
-    while len(pool) < n:
+    while len(pool) < min(n, MAX_SIDE_STREAMS):
         pool.append(torch.cuda.Stream(device=device))
-    return pool[:n]
+    return [pool[i % MAX_SIDE_STREAMS] for i in range(n)]
 
 
 def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
-                   g_color, g_depth, g_alpha, out=None, accumulate=False, raw: int = 0):
+                   g_color, g_depth, g_alpha, out=None, accumulate=False, raw: int = 0, tanfov_dev=None):
     lib = _lib.load()
     device = means3D.device
     P, K, H, W = sv.P, sv.K, sv.H, sv.W
     with torch.cuda.device(device):
         ws = _workspace(device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        s, keep = _make_settings(rs, device, raw)
+        s, keep = _make_settings(rs, device, raw, tanfov_dev)
         scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
 
         def grad_in(g, shape):
@@ -393,7 +441,7 @@ def _backward_impl(rs, sv: _Saved, means3D, shs, colors, opacities, scales, rota
 
 
 def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales, rotations, cov3D, radii,
-                    g_color, g_depth, g_alpha, exchange=None, raw: int = 0):
+                    g_color, g_depth, g_alpha, exchange=None, raw: int = 0, tanfov_dev=None):
     """Backward of V views: the blend backward of view v runs on side stream v (they overlap);
     the per-Gaussian stage runs view after view on the calling stream because it accumulates
     (beta = 1) into one set of gradient tensors."""
@@ -430,33 +478,38 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
         g_color, g_depth, g_alpha = grad_in(g_color, (V, 3, H, W)), grad_in(g_depth, (V, 1, H, W)), \
             grad_in(g_alpha, (V, 1, H, W))
         streams = _streams_for(device, V)
-        fork = torch.cuda.Event()
-        fork.record(main)
-        staged = []
-        for v, (rs, sv, st) in enumerate(zip(settings_list, svs, streams)):
-            st.wait_event(fork)
-            with torch.cuda.stream(st):
-                ws = _workspace(device)
-                s, keep = _make_settings(rs, device, raw)
-                scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
-                rc = lib.gsb_render_bwd(C.byref(s), P, sv.block.data_ptr(), scratch.data_ptr(), sv.d_cap,
-                                        g_color[v].data_ptr(), g_depth[v].data_ptr(), g_alpha[v].data_ptr(),
-                                        st.cuda_stream)
-                _lib.check(rc, "gsb_render_bwd")
-                done = torch.cuda.Event()
-                done.record(st)
-            staged.append((s, keep, scratch, done))
-        # one fused per-Gaussian kernel over all views: contributions summed in registers, every
-        # gradient tensor written once (instead of V read-modify-write passes)
-        for v, sv in enumerate(svs):
-            main.wait_event(staged[v][3])
-            sv.block.record_stream(main)
-        for v0 in range(0, V, _lib.MAX_VIEWS):
-            n = min(_lib.MAX_VIEWS, V - v0)
-            sp = (C.POINTER(_lib.GsbSettings) * n)(*[C.pointer(staged[v0 + j][0]) for j in range(n)])
+        # Groups of <= MAX_VIEWS views: their blend backwards run on the side streams (they overlap), then ONE fused
+        # per-Gaussian kernel sums the group's contributions in registers and writes (first group) or accumulates
+        # (later groups) every gradient tensor.  A side stream's scratch block holds the GGrad records of one view
+        # at a time, so the next group's blend backward waits for this group's per-Gaussian kernel.
+        G = min(_lib.MAX_VIEWS, MAX_SIDE_STREAMS)
+        for v0 in range(0, V, G):
+            n = min(G, V - v0)
+            fork = torch.cuda.Event()
+            fork.record(main)                # after the previous group's per-Gaussian kernel (and the exchange zeroing)
+            staged = []
+            for j in range(n):
+                v = v0 + j
+                rs, sv, st = settings_list[v], svs[v], streams[v]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    ws = _workspace(device)
+                    s, keep = _make_settings(rs, device, raw, None if tanfov_dev is None else tanfov_dev[v])
+                    scratch = ws.ensure_scratch(sv.layout.scratch_bytes)
+                    rc = lib.gsb_render_bwd(C.byref(s), P, sv.block.data_ptr(), scratch.data_ptr(), sv.d_cap,
+                                            g_color[v].data_ptr(), g_depth[v].data_ptr(), g_alpha[v].data_ptr(),
+                                            st.cuda_stream)
+                    _lib.check(rc, "gsb_render_bwd")
+                    done = torch.cuda.Event()
+                    done.record(st)
+                staged.append((s, keep, scratch, done))
+            for j in range(n):
+                main.wait_event(staged[j][3])
+                svs[v0 + j].block.record_stream(main)
+            sp = (C.POINTER(_lib.GsbSettings) * n)(*[C.pointer(staged[j][0]) for j in range(n)])
             rp = (C.c_void_p * n)(*[radii[v0 + j].data_ptr() for j in range(n)])
             svp = (C.c_void_p * n)(*[svs[v0 + j].block.data_ptr() for j in range(n)])
-            scp = (C.c_void_p * n)(*[staged[v0 + j][2].data_ptr() for j in range(n)])
+            scp = (C.c_void_p * n)(*[staged[j][2].data_ptr() for j in range(n)])
             dcp = (C.c_longlong * n)(*[svs[v0 + j].d_cap for j in range(n)])
             rc = lib.gsb_preprocess_bwd_views(n, sp, P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
                                               _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), rp, svp, scp,
@@ -472,9 +525,9 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
                 out = {k: (None if t is None else t.clone()) for k, t in out.items()}
         # the side streams' scratch blocks are read by the calling stream above; they are persistent
         # per-(device, stream) workspaces, so no allocator hand-over is involved
-        for st in streams[:V]:
-            back = torch.cuda.Event()
-            back.record(main)
+        back = torch.cuda.Event()
+        back.record(main)
+        for st in set(streams):
             st.wait_event(back)              # next use of a side workspace is ordered after these reads
     return out
 
@@ -551,10 +604,12 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                settings_list, exchange=None, raw=0):
+                settings_list, exchange=None, raw=0, tanfov_dev=None):
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = _prepare_inputs(
             means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         ctx.exchange = exchange
+        ctx.tanfov_dev = tanfov_dev
+        tf = (lambda v: None) if tanfov_dev is None else (lambda v: tanfov_dev[v])
         ctx.raw = raw = int(raw)
         if cov3Ds_precomp is not None:
             raw &= ~(_lib.RAW_SCALE | _lib.RAW_ROTATION)
@@ -578,22 +633,28 @@ class _RasterizeViews(torch.autograd.Function):
             streams = _streams_for(dev, V)
             fork = torch.cuda.Event()
             fork.record(main)
-            calls = []
-            for v, (rs, st) in enumerate(zip(settings_list, streams)):
+            for st in set(streams):
                 st.wait_event(fork)
-                with torch.cuda.stream(st):
-                    calls.append(_ForwardCall(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
-                                              cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]),
-                                              raw=raw).enqueue())
-            for call, st in zip(calls, streams):
-                svs.append(call.finish()[4])
+            # groups of MAX_SIDE_STREAMS views: a stream's counts block / event belongs to one pending view at a time
+            for v0 in range(0, V, MAX_SIDE_STREAMS):
+                calls = []
+                for v in range(v0, min(V, v0 + MAX_SIDE_STREAMS)):
+                    with torch.cuda.stream(streams[v]):
+                        calls.append(_ForwardCall(settings_list[v], means3D, sh, colors_precomp, opacities, scales,
+                                                  rotations, cov3Ds_precomp,
+                                                  out=(color[v], radii[v], depth[v], alpha[v]), raw=raw,
+                                                  tanfov_dev=tf(v)).enqueue())
+                for call in calls:
+                    svs.append(call.finish()[4])
+            for st in set(streams):
                 join = torch.cuda.Event()
                 join.record(st)
                 main.wait_event(join)
         else:
             for v, rs in enumerate(settings_list):
                 _, _, _, _, sv = _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
-                                               cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]), raw=raw)
+                                               cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]), raw=raw,
+                                               tanfov_dev=tf(v))
                 svs.append(sv)
         ctx.settings_list, ctx.svs = list(settings_list), svs
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,
@@ -614,9 +675,10 @@ class _RasterizeViews(torch.autograd.Function):
             out = _backward_views(ctx.settings_list, ctx.svs, means3D, sh if has_sh else None,
                                   colors if has_col else None, opacities, scales if has_sc else None,
                                   rotations if has_rot else None, cov3D if has_cov else None, radii,
-                                  grad_color, grad_depth, grad_alpha, exchange=ctx.exchange, raw=ctx.raw)
+                                  grad_color, grad_depth, grad_alpha, exchange=ctx.exchange, raw=ctx.raw,
+                                  tanfov_dev=ctx.tanfov_dev)
             return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
-                    out["rotations"], out["cov3D"], None, None, None)
+                    out["rotations"], out["cov3D"], None, None, None, None)
         out = None
         for v, (rs, sv) in enumerate(zip(ctx.settings_list, ctx.svs)):
             out = _backward_impl(rs, sv, means3D, sh if has_sh else None, colors if has_col else None, opacities,
@@ -625,27 +687,33 @@ class _RasterizeViews(torch.autograd.Function):
                                  None if grad_color is None else grad_color[v],
                                  None if grad_depth is None else grad_depth[v],
                                  None if grad_alpha is None else grad_alpha[v], out=out, accumulate=v > 0,
-                                 raw=ctx.raw)
+                                 raw=ctx.raw, tanfov_dev=None if ctx.tanfov_dev is None else ctx.tanfov_dev[v])
         return (out["means3D"], out["means2D"], out["shs"], out["colors"], out["opacities"], out["scales"],
-                out["rotations"], out["cov3D"], None, None, None)
+                out["rotations"], out["cov3D"], None, None, None, None)
 
 
 def rasterize_views(settings_list, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
-                    rotations=None, cov3D_precomp=None, exchange=None, raw_inputs: int = 0):
+                    rotations=None, cov3D_precomp=None, exchange=None, raw_inputs: int = 0, tanfov_dev=None):
     """Batched form of GaussianRasterizer(...)(...): returns stacked (color [V,3,H,W], radii [V,P],
     depth [V,1,H,W], alpha [V,1,H,W]); means2D.grad receives the SUM over views.  With
     ``exchange`` (gaussianip_b200.exchange.GradExchange) the input gradients returned by the backward
     are already summed over the ranks of the exchange's group (reduction fused into the kernel).
     ``raw_inputs`` (bits _lib.RAW_OPACITY | RAW_SCALE | RAW_ROTATION): the flagged inputs are the model's raw
     parameters (logits / log-scales / unnormalised quaternions); the kernels apply sigmoid / exp / normalize
-    and the returned gradients are with respect to the raw tensors (include/gsb.h GSB_RAW_*)."""
+    and the returned gradients are with respect to the raw tensors (include/gsb.h GSB_RAW_*).
+    ``tanfov_dev`` (optional, one device tensor [2] = (tanfovx, tanfovy) per view): the kernels read the intrinsics
+    from device memory instead of ``settings.tanfovx / tanfovy`` — needed when the call is captured in a CUDA
+    graph and replayed with other cameras (gaussianip_b200.graph, cameras.CameraBlock)."""
+    if tanfov_dev is not None and len(tanfov_dev) != len(settings_list):
+        raise ValueError("tanfov_dev needs one entry per view")
     if (shs is None) == (colors_precomp is None):
         raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                 cov3D_precomp, tuple(settings_list), exchange, int(raw_inputs))
+                                 cov3D_precomp, tuple(settings_list), exchange, int(raw_inputs),
+                                 None if tanfov_dev is None else tuple(tanfov_dev))
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

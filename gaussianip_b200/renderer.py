@@ -140,7 +140,8 @@ def render_views(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0
     image, radii_v, depth, alpha = rasterize_views(
         settings, means3D=xyz.float(), means2D=screenspace_points.float(), shs=f(shs),
         colors_precomp=colors_precomp, opacities=opacities.float(), scales=f(scales),
-        rotations=f(rotations), cov3D_precomp=cov3D_precomp, exchange=exchange, raw_inputs=raw)
+        rotations=f(rotations), cov3D_precomp=cov3D_precomp, exchange=exchange, raw_inputs=raw,
+        tanfov_dev=[cam.tanfov_dev for cam in cameras] if all(hasattr(cam, "tanfov_dev") for cam in cameras) else None)
     radii = radii_v.max(dim=0).values
     return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii, "radii_per_view": radii_v, "depth_3dgs": depth, "alpha_3dgs": alpha}

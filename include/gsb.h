@@ -58,6 +58,9 @@ typedef struct GsbSettings {
   const float* viewmatrix;   /* [16] device, column-major world->view (row-vector convention) */
   const float* projmatrix;   /* [16] device, column-major full projection */
   const float* campos;       /* [3]  device */
+  const float* tanfov_dev;   /* optional [2] device = {tanfovx, tanfovy}; when non-NULL the kernels read the intrinsics
+                                from here instead of the two by-value fields above (which must still be > 0), so a
+                                CUDA graph captured over these calls can be replayed with new cameras */
 } GsbSettings;
 
 /* Byte offsets of every sub-buffer inside the two blocks the HOST allocates per call

@@ -18,3 +18,19 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """GPU runs: keep the parity statistics the tests collected (per-element gradient errors, contributor-count
+    mismatch rates) as gpurun_out/parity_report.json."""
+    try:
+        import json
+        mod = sys.modules.get("tests.test_gpu_parity")
+        rep = getattr(mod, "REPORT", None) if mod is not None else None
+        if rep:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_report.json"), "w") as f:
+                json.dump(rep, f, indent=1, sort_keys=True)
+    except Exception:
+        pass

@@ -33,12 +33,56 @@ def _gpu_forward_state(scene, device, mode="two_level"):
     return color, radii, depth, alpha, sv, keys
 
 
+REPORT = {}          # written to gpurun_out/parity_report.json at the end of the session (tests/conftest.py)
+
+
 def _grad_close(name, got, ref, rtol=GRAD_RTOL):
     got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()
     # relative to the tensor's largest gradient (atomic accumulation order differs per element)
     assert err <= rtol * max(scale, 1e-12), f"{name}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+# Per-element bar next to the max-norm one: |got - ref| <= 1e-4 |ref| + atol with atol = ATOL_MEAN x mean |ref| of the
+# tensor's non-zero entries.  Why an absolute term at all: an entry is a sum over the Gaussian's pixels of signed terms
+# (the loss weights are N(0,1)), accumulated in a different order on the GPU (atomics) and with ex2.approx instead of
+# exp; the rounding error scales with the magnitude of the TERMS, not of the possibly cancelled sum, and the mean
+# |gradient| of the tensor is the natural size of such a sum.  Why the mean and not the max: the max-norm bar lets an
+# entry 1000x below the maximum be 10 % wrong; against the mean an entry of typical size must be right to 1e-4 and
+# one 100x below typical to 1 %.
+ATOL_MEAN = 1e-4
+
+
+def _grad_close_elementwise(case, name, got, ref, rtol=GRAD_RTOL, atol_mean=ATOL_MEAN):
+    got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
+    nz = ref != 0
+    mean = ref[nz].abs().mean().item() if bool(nz.any()) else 0.0
+    err = (got - ref).abs()
+    excess = err - rtol * ref.abs()                  # what the absolute term has to cover
+    need = (excess.max().item() / mean) if mean > 0 else 0.0
+    pure_rel_viol = float((err > rtol * ref.abs()).double().mean().item())
+    REPORT.setdefault("gradients", {})[f"{case}/{name}"] = {
+        "max_abs_err": err.max().item(), "max_abs_ref": ref.abs().max().item(), "mean_abs_ref": mean,
+        "atol_needed_in_units_of_mean": need, "fraction_outside_pure_1e-4_relative": pure_rel_viol,
+        "wrong_zero_pattern": int(((ref == 0) & (got != 0)).sum().item())}
+    bad = excess > atol_mean * mean
+    assert not bool(bad.any()), (f"{case}/{name}: {int(bad.sum())} entries outside 1e-4 |ref| + {atol_mean:g} mean|ref| "
+                                 f"(needs {need:.3g} x mean)")
+
+
+def _n_contrib_report(case, got_nc, img):
+    """Mismatch RATES of the per-pixel contributor counts, on pixels the oracle can decide and on the ones it flags
+    as marginal (an alpha >= 1/255 or T < 1e-4 decision inside fp32 exp noise: no CPU oracle can decide those)."""
+    mism = got_nc != img.n_contrib
+    marg = img.marginal
+    n_ok, n_marg = int((~marg).sum()), int(marg.sum())
+    r = {"pixels": int(marg.numel()), "marginal_pixels": n_marg,
+         "mismatch_rate_non_marginal": float((mism & ~marg).sum()) / max(1, n_ok),
+         "mismatch_rate_marginal": float((mism & marg).sum()) / max(1, n_marg),
+         "mismatches_non_marginal": int((mism & ~marg).sum()), "mismatches_marginal": int((mism & marg).sum())}
+    REPORT.setdefault("n_contrib", {})[case] = r
+    return r
 
 
 SCENES = {
@@ -85,10 +129,8 @@ def test_forward_exact_and_tolerance(cuda_device, name, mode):
     assert (alpha.cpu() - ref["alpha"]).abs().max().item() <= FWD_ATOL
     # contributor counts: exact, except pixels where the oracle itself flags a threshold decision
     # (alpha >= 1/255 or T < 1e-4) that sits inside fp32 exp/rounding noise
-    nc = sv.n_contrib().cpu()
-    mism = (nc != img.n_contrib) & ~img.marginal
-    assert int(mism.sum()) == 0, f"{int(mism.sum())} unflagged n_contrib mismatches"
-    assert float(img.marginal.float().mean()) < 0.05
+    rep = _n_contrib_report(f"{name}/{mode}", sv.n_contrib().cpu(), img)
+    assert rep["mismatches_non_marginal"] == 0, f"{rep['mismatches_non_marginal']} unflagged n_contrib mismatches"
     ok = ~img.marginal
     torch.testing.assert_close(sv.final_T().cpu()[ok], img.final_T[ok], rtol=2e-4, atol=1e-6)
 
@@ -105,6 +147,7 @@ def test_backward_tolerance(cuda_device, name):
         gg = got["grads"][k]
         assert gg is not None, f"no gradient for {k}"
         _grad_close(k, gg, rg)
+        _grad_close_elementwise(name, k, gg, rg)
     # means2D grad is (x, y, 0)
     assert float(got["grads"]["means2D"][:, 2].abs().max()) == 0.0
     # culled Gaussians get exactly zero gradient
