@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--sh-degree", type=int, default=None)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: on, falling back to eager enqueue if capture fails)")
-    ap.add_argument("--variant", default="native", choices=["native", "standin", "packed_bwd"],
+    ap.add_argument("--variant", default="native", choices=["native", "standin", "packed_bwd", "rescan_bwd", "rescan_packed_bwd"],
                     help="standin = reference-STRUCTURE kernels of csrc/standin.cu + 64-bit key sort + per-view "
                          "Python loop, for context only (never the reference, never the product)")
     ap.add_argument("--view-sharding", default="interleaved", choices=["balanced", "interleaved"],
@@ -699,8 +699,8 @@ def training_arm(a, rank, world, local_rank):
     if standin:
         rasterizer.set_blend_variant("standin")
         rasterizer.set_binning_mode("flat64", dev)
-    elif a.variant == "packed_bwd":
-        rasterizer.set_blend_variant("packed_bwd")
+    elif a.variant != "native":
+        rasterizer.set_blend_variant(a.variant)
     use_graph = a.graph != "off" and not standin
     total_steps = a.warmup + a.steps + 8
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -754,7 +754,7 @@ def training_arm(a, rank, world, local_rank):
 
     line = {"variant": "reference-STRUCTURE stand-in (csrc/standin.cu + flat 64-bit sort + per-view loop); NOT the "
                        "reference and NOT the product path"} if standin else (
-        {"variant": "EXPERIMENTAL packed-reduction backward (gsb_set_blend_variant(2))"} if a.variant == "packed_bwd" else {})
+        {"variant": f"backward blend variant {a.variant} (gsb_set_blend_variant)"} if a.variant != "native" else {})
     if fused:
         par = (f"view-sharded dp{world}, gradients reduced INSIDE the backward kernel ({wl.vp.exchange.algorithm} over "
                f"NVLink peer / NVLS multicast memory, {wl.vp.exchange.nbytes() >> 20} MiB) + NCCL radii max per step")
@@ -851,18 +851,19 @@ def playback_arm(a, rank, world, local_rank):
         def __init__(self):
             self.image_width, self.image_height, self.FoVx, self.FoVy = cam0.image_width, cam0.image_height, cam0.FoVx, cam0.FoVy
             self.znear, self.zfar = cam0.znear, cam0.zfar
-            self.world_view_transform = cam0.world_view_transform.clone()
-            self.projection_matrix = cam0.projection_matrix.clone()
-            self.full_proj_transform = cam0.full_proj_transform.clone()
-            self.camera_center = cam0.camera_center.clone()
+            self.world_view_transform = cam0.world_view_transform.contiguous().clone()
+            self.projection_matrix = cam0.projection_matrix.contiguous().clone()
+            self.full_proj_transform = cam0.full_proj_transform.contiguous().clone()
+            self.camera_center = cam0.camera_center.contiguous().clone()
     scam = StaticCam()
-    cam_stage = torch.stack([torch.cat((c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+    cam_stage = torch.stack([torch.cat((c.world_view_transform.contiguous().reshape(-1),
+                                        c.full_proj_transform.contiguous().reshape(-1),
                                         c.camera_center.reshape(-1))) for c in cams_all]).contiguous()   # [136, 35] device
 
     def set_cam(f):
         row = cam_stage[f % n_frames]
-        scam.world_view_transform.view(-1).copy_(row[0:16])
-        scam.full_proj_transform.view(-1).copy_(row[16:32])
+        scam.world_view_transform.copy_(row[0:16].view(4, 4))
+        scam.full_proj_transform.copy_(row[16:32].view(4, 4))
         scam.camera_center.copy_(row[32:35])
 
     def frame(slot):

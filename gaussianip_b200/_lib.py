@@ -19,13 +19,14 @@ class GsbSettings(C.Structure):
     _fields_ = [("image_height", C.c_int32), ("image_width", C.c_int32),
                 ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
                 ("sh_degree", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
-                ("raw_inputs", C.c_int32),
+                ("raw_inputs", C.c_int32), ("forward_only", C.c_int32),
                 ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
                 ("campos", C.c_void_p), ("tanfov_dev", C.c_void_p)]
 
 
 _LAYOUT_FIELDS = ["saved_bytes", "off_geom", "off_clamped", "off_counts", "off_point_list", "off_ranges",
-                  "off_n_contrib", "off_final_T", "off_tile_order", "scratch_bytes", "off_rect", "off_tiles", "off_dkeys0",
+                  "off_n_contrib", "off_final_T", "off_tile_order", "off_hit_count", "off_hits",
+                  "saved_bytes_forward_only", "scratch_bytes", "off_rect", "off_tiles", "off_dkeys0",
                   "off_dkeys1", "off_dkeys2", "off_didx0", "off_didx1", "off_offsets", "off_blocksums",
                   "off_hist", "off_tkeys0", "off_tkeys1", "off_tvals_alt", "off_keys64_0", "off_keys64_1",
                   "off_ggrad"]

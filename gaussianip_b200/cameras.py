@@ -66,8 +66,10 @@ class Camera:
         self.scale = scale
         self.data_device = torch.device(data_device)
         w2c = _w2c_from_c2w(c2w)
-        view = w2c.T
-        proj = projection_matrix(self.znear, self.zfar, self.FoVx, self.FoVy).T
+        # contiguous copies: torch.tensor keeps numpy's transposed strides, and a non-contiguous matrix would cost
+        # every render call a device copy before its pointer can be handed to the kernels
+        view = np.ascontiguousarray(w2c.T)
+        proj = np.ascontiguousarray(projection_matrix(self.znear, self.zfar, self.FoVx, self.FoVy).T)
         full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
         center = np.linalg.inv(view)[3, :3]
         dev = self.data_device
@@ -194,8 +196,8 @@ class MiniCam:
         self.zfar = zfar
         c2w = np.asarray(c2w, dtype=np.float64)
         w2c = _w2c_from_c2w(c2w)
-        view = w2c.T
-        proj = projection_matrix(znear, zfar, self.FoVx, self.FoVy).T
+        view = np.ascontiguousarray(w2c.T)
+        proj = np.ascontiguousarray(projection_matrix(znear, zfar, self.FoVx, self.FoVy).T)
         full = view.astype(np.float32).astype(np.float64) @ proj.astype(np.float32).astype(np.float64)
         dev = torch.device(data_device)
         self.world_view_transform = torch.tensor(view, dtype=torch.float32).to(dev)

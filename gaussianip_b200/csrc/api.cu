@@ -82,6 +82,9 @@ static int layout(int P, int H, int W, long long D_cap, GsbLayout* L) {
   L->off_n_contrib = take(HW * 4);
   L->off_final_T = take(HW * 4);
   L->off_tile_order = take(T * 4);
+  L->off_hit_count = take(T * 8 * 4);
+  L->saved_bytes_forward_only = o;
+  L->off_hits = take(Dz * 8 * sizeof(uint2));
   L->saved_bytes = o;
   o = 0;
   L->off_rect = take(Pz * 8);
@@ -178,7 +181,7 @@ int gsb_adam_step(int n_groups, float* const* params, const float* const* grads,
 }
 
 int gsb_set_blend_variant(int variant) {
-  if (variant < 0 || variant > 2) return GSB_E_INVALID;
+  if (variant < 0 || variant > 4) return GSB_E_INVALID;
   g_blend_variant.store(variant);
   return GSB_OK;
 }
@@ -230,10 +233,13 @@ int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap, fl
                               at<uint2>(saved, L.off_ranges), out_color, out_depth, out_alpha,
                               at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
                               (cudaStream_t)stream);
+  const bool record = s->forward_only == 0;
   return launch_render_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order), out_color,
                            out_depth, out_alpha,
-                           at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
+                           at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T),
+                           record ? at<uint2>(saved, L.off_hits) : nullptr,
+                           record ? at<uint32_t>(saved, L.off_hit_count) : nullptr, s->debug != 0,
                            (cudaStream_t)stream);
 }
 
@@ -274,11 +280,16 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
                               at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_n_contrib),
                               at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
                               at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
+  if (s->forward_only) return GSB_E_INVALID;       // that forward kept nothing for a backward pass
+  // variants: 0 replay + butterfly (default), 2 replay + packed reduction, 3 rescan + butterfly (the round-1
+  // kernel, record-free), 4 rescan + packed reduction
+  const int variant = g_blend_variant.load();
   return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order),
-                           at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
-                           at<GGrad>(scratch, L.off_ggrad), g_blend_variant.load() == 2, s->debug != 0,
-                           (cudaStream_t)stream);
+                           at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T),
+                           at<uint2>(saved, L.off_hits), at<uint32_t>(saved, L.off_hit_count), dL_dcolor, dL_ddepth,
+                           dL_dalpha, at<GGrad>(scratch, L.off_ggrad), variant == 0 || variant == 2,
+                           variant == 2 || variant == 4, s->debug != 0, (cudaStream_t)stream);
 }
 
 int gsb_preprocess_bwd_views(int V, const GsbSettings* const* settings, int P, int K, const float* means3D,

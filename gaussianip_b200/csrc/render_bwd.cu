@@ -1,6 +1,16 @@
 // Backward stage 1: per-pixel reverse (back-to-front) blending.  Replaces renderCUDA
 // (backward) of the external operator ("Backward blend").
 //
+// Two kernels:
+//  * render_bwd_replay_kernel (default): walks, back to front, the HIT RECORDS the forward blend wrote per warp
+//    ({Gaussian id, mask of the lanes that blended it}, render_fwd.cu).  Every record is a Gaussian at least one
+//    pixel of the warp really blended, the mask says which, so nothing is culled, rect-tested or alpha-tested
+//    again: of the round-1 kernel's ~276 M warp instructions per view, the list walk (7.7 M candidates), the
+//    rectangle tests and the 1.5 M whole-warp alpha evaluations that only decide validity are gone.
+//  * render_bwd_kernel (gsb_set_blend_variant(3/4), "rescan"): the round-1 kernel, which needs no records and
+//    re-walks the tile list with per-warp culling.  Kept as the cross-check of the replay kernel.
+//
+// Rescan kernel:
 // Same organisation as render_fwd.cu: one CTA per 16x16 tile, warp = 8x4 pixels, warps fully
 // independent (no __syncthreads), per-warp cp.async ring of 32-instance chunks, per-warp
 // conservative culling.  Differences that matter:
@@ -10,7 +20,9 @@
 //    13-shuffle multi-value butterfly and leave the SM as ONE red.global per component per
 //    (warp, Gaussian) — 10 lanes hitting one 48 B GGrad record — instead of ~10 atomicAdd
 //    per (pixel, Gaussian).
+#include <atomic>
 #include <cstdio>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -30,7 +42,11 @@ constexpr int STAGES = GSB_BWD_STAGES;
 #ifndef GSB_BWD_HB
 #define GSB_BWD_HB 1
 #endif
-constexpr int BH = GSB_BWD_HB;       // hits evaluated together
+constexpr int BH = GSB_BWD_HB;       // hits evaluated together (rescan kernel)
+#ifndef GSB_BWD_RB
+#define GSB_BWD_RB 1
+#endif
+constexpr int RB = GSB_BWD_RB;       // records replayed together (replay kernel)
 
 // EXPERIMENTAL variant (gsb_set_blend_variant(2), not the default; passed gradient parity on one scene, not yet
 // benchmarked — DESIGN.md §8.1):
@@ -319,12 +335,191 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 #endif
 }
 
+
+// ---- replay kernel --------------------------------------------------------------------------------------------
+// Same per-pixel state and arithmetic as the rescan kernel (T rebuilt backwards from final_T, one suffix scalar
+// Bdot), same raw-moment outputs; the iteration space is the warp's record list instead of the tile's instance list.
+// Records are fetched 32 at a time (one coalesced 256 B load, lane l <- record l), their Geom rows gathered with
+// cp.async into the same 2-stage ring, one block of records ahead of the arithmetic.
+template <bool PACKED>
+__global__ void __launch_bounds__(WARPS * 32)
+render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __restrict__ ranges,
+                         const uint32_t* __restrict__ tile_order, const uint2* __restrict__ hits,
+                         const uint32_t* __restrict__ hit_count, const float* __restrict__ final_T,
+                         const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
+                         const float* __restrict__ dL_dalpha, GGrad* __restrict__ ggrad) {
+  extern __shared__ float4 smem_dyn[];
+  float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
+  uint2 (*s_meta)[STAGES][32] = reinterpret_cast<uint2 (*)[STAGES][32]>(smem_dyn + WARPS * STAGES * 3 * 32);
+  char* packed_base = reinterpret_cast<char*>(smem_dyn) + (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint2));
+
+  const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
+  const int tx = tile % v.gx, ty = tile / v.gx;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_rec = (int)hit_count[tile * WARPS + warp];
+  if (n_rec == 0) return;
+  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  float* slab = reinterpret_cast<float*>(packed_base + (size_t)warp * PACKED_WARP_BYTES);
+  int* seg_start = reinterpret_cast<int*>(slab + SLAB * SLAB_STRIDE);        // [SEG_MAX + 2]
+  uint32_t* seg_gid = reinterpret_cast<uint32_t*>(seg_start + SEG_MAX + 2);  // [SEG_MAX]
+  int n_pairs = 0, n_seg = 0;                                                // warp-uniform
+  const int pix_x = tx * TILE_X + wx + (lane & 7);
+  const int pix_y = ty * TILE_Y + wy + (lane >> 3);
+  const bool inside = pix_x < v.W && pix_y < v.H;
+  const float pxf = (float)pix_x, pyf = (float)pix_y;
+  const size_t hw = (size_t)v.H * v.W;
+  const size_t pix = (size_t)pix_y * v.W + pix_x;
+  const uint2 range = ranges[tile];
+  const uint2* recs = hits + ((size_t)range.x * WARPS + (size_t)warp * (size_t)(range.y - range.x));
+  const int blocks = (n_rec + 31) >> 5;
+
+  const float T_final = inside ? final_T[pix] : 0.0f;
+  float T = T_final;
+  const float gC0 = inside ? dL_dcolor[pix] : 0.f, gC1 = inside ? dL_dcolor[hw + pix] : 0.f,
+              gC2 = inside ? dL_dcolor[2 * hw + pix] : 0.f;
+  const float gD = inside ? dL_ddepth[pix] : 0.f, gA = inside ? dL_dalpha[pix] : 0.f;
+  const float bg_dot = v.bg[0] * gC0 + v.bg[1] * gC1 + v.bg[2] * gC2;
+  float Bdot = T_final * bg_dot;
+
+  float4 (*ring)[3][32] = s_rec[warp];
+  uint2 (*mring)[32] = s_meta[warp];
+  // block index c counts from the BACK: it covers records [(blocks-1-c)*32, +32)
+  auto fetch_rec = [&](int c) -> uint2 {
+    if (c >= blocks) return make_uint2(0u, 0u);
+    const int e = (blocks - 1 - c) * 32 + lane;
+    return e < n_rec ? recs[e] : make_uint2(0u, 0u);
+  };
+  auto issue = [&](int c, uint2 rec) {
+    if (c < blocks) {
+      const int e = (blocks - 1 - c) * 32 + lane;
+      if (e < n_rec) {
+        const float4* src = reinterpret_cast<const float4*>(geom + rec.x);
+        float4 (*st)[32] = ring[c & (STAGES - 1)];
+        cp_async16(&st[0][lane], src);
+        cp_async16(&st[1][lane], src + 1);
+        cp_async16(&st[2][lane], src + 2);
+        mring[c & (STAGES - 1)][lane] = rec;
+      }
+    }
+    cp_async_commit();
+  };
+  auto flush = [&]() {
+    if (lane == 0) seg_start[n_seg] = n_pairs;          // end sentinel
+    __syncwarp();
+    const int grp = lane / 10, comp = lane - grp * 10;    // lanes 30, 31 (grp 3) idle
+    for (int h0 = 0; h0 < n_seg; h0 += 3) {
+      const int h = h0 + grp;
+      if (grp < 3 && h < n_seg) {
+        const int a = seg_start[h], b = seg_start[h + 1];
+        float sum = 0.0f;
+        for (int sl = a; sl < b; ++sl) sum += slab[sl * SLAB_STRIDE + comp];
+        if (sum != 0.0f) atomicAdd(reinterpret_cast<float*>(ggrad + seg_gid[h]) + comp, sum);
+      }
+    }
+    __syncwarp();
+    n_pairs = 0; n_seg = 0;
+  };
+#pragma unroll
+  for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_rec(c));
+  uint2 rec_next = fetch_rec(STAGES - 1);
+
+  const int slot = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+  const bool writer = !(lane & 1) && !((lane & 4) && (lane & 2)) && slot < 10;
+  for (int c = 0; c < blocks; ++c) {
+    issue(c + STAGES - 1, rec_next);
+    rec_next = fetch_rec(c + STAGES);
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    float4 (*st)[32] = ring[c & (STAGES - 1)];
+    const uint2* meta = mring[c & (STAGES - 1)];
+    const int base = (blocks - 1 - c) * 32;
+    const int nb = min(32, n_rec - base);
+    // RB records at a time: their loads, Gaussian weights and 13-shuffle reductions are independent and overlap;
+    // only the short transmittance / suffix-sum chain runs in order.  The replay kernel is bound by its longest
+    // warps (a heavy tile's warp replays ~1e3 records one after the other), so the latency of one record's chain
+    // matters more than registers here.
+    for (int r = nb - 1; r >= 0; r -= RB) {
+      uint2 mr[RB];
+      bool valid[RB];
+      float dx[RB], dy[RB], G[RB], alpha[RB];
+      float4 q[RB], f[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int ri = r - i;
+        valid[i] = false;
+        mr[i] = make_uint2(0u, 0u);
+        if (ri >= 0) {
+          mr[i] = meta[ri];                               // {Gaussian id, lanes that blended it}: warp-uniform
+          valid[i] = (mr[i].y >> lane) & 1u;
+          const float4 a = st[0][ri];
+          q[i] = st[1][ri];
+          f[i] = st[2][ri];
+          dx[i] = a.x - pxf; dy[i] = a.y - pyf;
+          G[i] = exp2_blend(gauss_exponent2(q[i].x, q[i].y, q[i].z, dx[i], dy[i]));
+          alpha[i] = fminf(ALPHA_CAP, q[i].w * G[i]);
+        }
+      }
+      float g[RB][12];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) g[i][j] = 0.0f;
+        if (valid[i]) {
+          const float inv1ma = rcp_blend(1.0f - alpha[i]);
+          T *= inv1ma;
+          const float w = alpha[i] * T;
+          const float phi = f[i].y * gC0 + f[i].z * gC1 + f[i].w * gC2 + f[i].x * gD + gA;
+          const float dL_da = T * phi - Bdot * inv1ma;
+          Bdot += phi * w;
+          const float s_ = q[i].w * dL_da * G[i];
+          g[i][0] = s_ * dx[i];
+          g[i][1] = s_ * dy[i];
+          g[i][2] = g[i][0] * dx[i];
+          g[i][3] = g[i][0] * dy[i];
+          g[i][4] = g[i][1] * dy[i];
+          g[i][5] = G[i] * dL_da;
+          g[i][6] = w * gD;
+          g[i][7] = w * gC0;
+          g[i][8] = w * gC1;
+          g[i][9] = w * gC2;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        if (r - i < 0) continue;
+        if (PACKED) {
+          const int nv = __popc(mr[i].y);
+          if (n_pairs + nv > SLAB || n_seg == SEG_MAX) flush();
+          if (lane == 0) { seg_start[n_seg] = n_pairs; seg_gid[n_seg] = mr[i].x; }
+          if (valid[i]) {
+            float* dst = slab + (n_pairs + __popc(mr[i].y & ((1u << lane) - 1u))) * SLAB_STRIDE;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) dst[j] = g[i][j];
+          }
+          n_pairs += nv; ++n_seg;
+        } else {
+          const float tot = butterfly12(g[i], lane);
+#ifdef GSB_BWD_NO_RED      // diagnostic build only (timing without the global reductions; results are wrong)
+          if (writer && tot == 123.456f) atomicAdd(reinterpret_cast<float*>(ggrad + mr[i].x) + slot, tot);
+#else
+          if (writer && tot != 0.0f) atomicAdd(reinterpret_cast<float*>(ggrad + mr[i].x) + slot, tot);
+#endif
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (PACKED && n_seg) flush();
+  cp_async_wait<0>();
+}
+
 }  // namespace
 
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
-                      const float* final_T, const float* dL_dcolor, const float* dL_ddepth,
-                      const float* dL_dalpha, GGrad* ggrad, bool packed, bool debug, cudaStream_t st) {
+                      const float* final_T, const uint2* hits, const uint32_t* hit_count, const float* dL_dcolor,
+                      const float* dL_ddepth, const float* dL_dalpha, GGrad* ggrad, bool replay, bool packed,
+                      bool debug, cudaStream_t st) {
   GSB_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)P * sizeof(GGrad), st));
   const int T = v.gx * v.gy;
   if (T == 0 || P == 0) return GSB_OK;
@@ -332,21 +527,36 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
 #define GSB_BWD_SMEM_PAD 0
 #endif
   // (padding = an occupancy cap for tuning sweeps: shared memory not used by CTAs stays L1)
-  constexpr size_t smem_ring = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
-  const size_t smem = smem_ring + (packed ? (size_t)WARPS * PACKED_WARP_BYTES : 0) + GSB_BWD_SMEM_PAD;
-  static bool configured[64] = {}, configured_packed[64] = {};   // the attribute is per device
+  constexpr size_t ring_rescan = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t));
+  constexpr size_t ring_replay = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint2));
+  constexpr size_t slab_bytes = (size_t)WARPS * PACKED_WARP_BYTES;
+  static std::atomic<unsigned long long> configured{0};   // bit per device: the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
-  if (!packed && !configured[dev & 63]) {
+  if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
     GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(smem_ring + GSB_BWD_SMEM_PAD)));
-    configured[dev & 63] = true;
-  }
-  if (packed && !configured_packed[dev & 63]) {
+                                  (int)(ring_rescan + GSB_BWD_SMEM_PAD)));
     GSB_CUDA(cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(smem_ring + WARPS * PACKED_WARP_BYTES + GSB_BWD_SMEM_PAD)));
-    configured_packed[dev & 63] = true;
+                                  (int)(ring_rescan + slab_bytes + GSB_BWD_SMEM_PAD)));
+    GSB_CUDA(cudaFuncSetAttribute(render_bwd_replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(ring_replay + GSB_BWD_SMEM_PAD)));
+    GSB_CUDA(cudaFuncSetAttribute(render_bwd_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(ring_replay + slab_bytes + GSB_BWD_SMEM_PAD)));
+    configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
+  if (replay) {
+    if (!hits || !hit_count) return GSB_E_INVALID;
+    const size_t smem = ring_replay + (packed ? slab_bytes : 0) + GSB_BWD_SMEM_PAD;
+    if (packed)
+      render_bwd_replay_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, ranges, tile_order, hits, hit_count, final_T,
+                                                                  dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
+    else
+      render_bwd_replay_kernel<false><<<T, WARPS * 32, smem, st>>>(v, geom, ranges, tile_order, hits, hit_count, final_T,
+                                                                   dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
+    GSB_POST_LAUNCH(debug, st, "render_bwd_replay_kernel");
+    return GSB_OK;
+  }
+  const size_t smem = ring_rescan + (packed ? slab_bytes : 0) + GSB_BWD_SMEM_PAD;
   if (packed)
     render_bwd_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, n_contrib, final_T,
                                                          dL_dcolor, dL_ddepth, dL_dalpha, ggrad);

@@ -9,11 +9,18 @@
 // pixels (conservative extent test, see preprocess.cu); the ballot gives the hit list and only
 // hits are evaluated, in list order, so results are identical to evaluating everything.  A
 // warp stops as soon as all of its pixels are saturated.
+// Hit records (RECORD): whenever at least one of the warp's pixels BLENDS a Gaussian, the warp appends
+// {Gaussian id, mask of the blending lanes} to its own record list in `saved` (GsbLayout.off_hits): per hit one
+// ballot and one shared-memory store of the mask (slot = the instance's position in the chunk), per chunk one
+// compaction of the non-zero masks into consecutive records.  The backward blend replays these lists back to
+// front and never re-tests or culls anything (render_bwd.cu).
 // Measured alternatives (profiles/r1_experiments.md): block-synchronous 256-instance batches lost
 // 44 % of issue slots to CTA barriers (r1a); deeper private rings are SLOWER (4 stages 241 us, 8
 // stages 318 us vs 232 us at 2: shared memory is taken from L1, which serves the 8 warps' re-reads
 // of the same records); one producer warp feeding a ring shared by the 8 consumers was slower too
 // (257-297 us: a single warp's gather latency cannot feed eight consumers).
+#include <atomic>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -38,14 +45,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+template <bool RECORD>
 __global__ void __launch_bounds__(WARPS * 32)
 render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                   float* __restrict__ out_color,
                   float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                  uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+                  uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
+                  uint2* __restrict__ hits, uint32_t* __restrict__ hit_count) {
   extern __shared__ float4 smem_dyn[];             // 12 KB per stage per CTA
   float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
+  // RECORD: per warp, the blend masks of the current chunk's 32 instances
+  uint32_t (*s_mask)[32] = reinterpret_cast<uint32_t (*)[32]>(smem_dyn + WARPS * STAGES * 3 * 32);
 
   const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
@@ -73,6 +84,9 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   // (the transmittance the reference reports as final_T).
   float T = inside ? 1.0f : 0.0f, T_live = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f, A = 0.f;
   uint32_t last = 0;
+  // hit records of this warp: capacity n (an instance yields at most one record per warp)
+  uint2* rec_base = RECORD ? hits + ((size_t)range.x * WARPS + (size_t)warp * (size_t)n) : nullptr;
+  int rec_n = 0;
 
   if (chunks > 0 && __any_sync(0xffffffffu, T != 0.0f)) {
     float4 (*ring)[3][32] = s_rec[warp];
@@ -93,13 +107,17 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       return (c < chunks && e < n) ? pl[e] : 0u;
     };
     // prologue: STAGES-1 chunks in flight, ids of the next one in a register
+    static_assert(!RECORD || STAGES == 2, "the record path keeps the ids of exactly one chunk in flight");
+    uint32_t gid_cur = fetch_gid(0);              // this lane's instance of the chunk being blended (RECORD)
 #pragma unroll
-    for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_gid(c));
+    for (int c = 0; c < STAGES - 1; ++c) issue(c, c == 0 ? gid_cur : fetch_gid(c));
     uint32_t gid_next = fetch_gid(STAGES - 1);
 
     for (int c = 0; c < chunks; ++c) {
+      const uint32_t gid_issued = gid_next;
       issue(c + STAGES - 1, gid_next);
       gid_next = fetch_gid(c + STAGES);
+      if (RECORD) s_mask[warp][lane] = 0u;
       cp_async_wait<STAGES - 1>();               // chunk c has landed (for this lane)
       __syncwarp();                              // ... and for every lane of the warp
       float4 (*st)[32] = ring[c & (STAGES - 1)];
@@ -145,9 +163,10 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
         }
 #pragma unroll
         for (int i = 0; i < HB; ++i) {
+          bool ok = false;
           if (k[i] >= 0 && al[i] >= ALPHA_MIN) {
             const float test_T = T * (1.0f - al[i]);
-            const bool ok = test_T >= T_MIN;
+            ok = test_T >= T_MIN;
             if (ok) {
               const float w = al[i] * T;
               C0 += ff[i].y * w; C1 += ff[i].z * w; C2 += ff[i].w * w;
@@ -157,13 +176,27 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
             }
             T = ok ? test_T : 0.0f;       // a saturating splat (or a finished pixel) leaves T at 0
           }
+          if (RECORD) {
+            const uint32_t vb = __ballot_sync(0xffffffffu, ok);     // the pixels that blended this Gaussian
+            if (lane == 0 && k[i] >= 0) s_mask[warp][k[i]] = vb;
+          }
         }
+      }
+      if (RECORD) {
+        // append this chunk's records: instance l of the chunk was blended by the pixels in s_mask[l]
+        __syncwarp();
+        const uint32_t m = s_mask[warp][lane];
+        const uint32_t nz = __ballot_sync(0xffffffffu, m != 0u);
+        if (m) rec_base[rec_n + __popc(nz & ((1u << lane) - 1u))] = make_uint2(gid_cur, m);
+        rec_n += __popc(nz);
+        gid_cur = gid_issued;
       }
       if (__all_sync(0xffffffffu, T == 0.0f)) break;
       __syncwarp();                              // ring slot c is free before it is refilled
     }
     cp_async_wait<0>();
   }
+  if (RECORD && lane == 0) hit_count[tile * WARPS + warp] = (uint32_t)rec_n;
 
   if (inside) {
     T = T_live;
@@ -183,22 +216,28 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 
 int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
-                      uint32_t* n_contrib, float* final_T, bool debug, cudaStream_t st) {
+                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool debug,
+                      cudaStream_t st) {
   const int T = v.gx * v.gy;
   if (T == 0) return GSB_OK;
 #ifndef GSB_FWD_SMEM_PAD
 #define GSB_FWD_SMEM_PAD 0
 #endif
-  constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4) + GSB_FWD_SMEM_PAD;
-  static bool configured[64] = {};   // the attribute is per device
+  constexpr size_t smem = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t)) + GSB_FWD_SMEM_PAD;
+  static std::atomic<unsigned long long> configured{0};   // bit per device: the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
-    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[dev & 63] = true;
+  if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
-  render_fwd_kernel<<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth, alpha,
-                                              n_contrib, final_T);
+  if (hits && hit_count)
+    render_fwd_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth,
+                                                         alpha, n_contrib, final_T, hits, hit_count);
+  else
+    render_fwd_kernel<false><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth,
+                                                          alpha, n_contrib, final_T, nullptr, nullptr);
   GSB_POST_LAUNCH(debug, st, "render_fwd_kernel");
   return GSB_OK;
 }

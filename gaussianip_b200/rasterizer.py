@@ -120,7 +120,8 @@ def _small(t: torch.Tensor, n: int, name: str, device) -> torch.Tensor:
     return t
 
 
-def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0, tanfov_dev: Optional[torch.Tensor] = None):
+def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0, tanfov_dev: Optional[torch.Tensor] = None,
+                   forward_only: bool = False):
     bg = _small(rs.bg, 3, "bg", device)
     view = _small(rs.viewmatrix, 16, "viewmatrix", device)
     proj = _small(rs.projmatrix, 16, "projmatrix", device)
@@ -129,14 +130,15 @@ def _make_settings(rs: GaussianRasterizationSettings, device, raw: int = 0, tanf
         raise ValueError("sh_degree must be in 0..3")
     s = _lib.GsbSettings(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
                          float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)),
-                         int(bool(rs.debug)), int(raw), bg.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                         int(bool(rs.debug)), int(raw), int(bool(forward_only)), bg.data_ptr(), view.data_ptr(), proj.data_ptr(),
                          campos.data_ptr(), None if tanfov_dev is None else _small(tanfov_dev, 2, "tanfov_dev", device).data_ptr())
     return s, (bg, view, proj, campos, tanfov_dev)      # keep the tensors alive next to the struct
 
 
 class _Saved:
     """Per-call state kept for backward (and exposed to the parity tests)."""
-    __slots__ = ("block", "layout", "d_cap", "P", "K", "H", "W", "num_rendered", "scratch", "settings_keep")
+    __slots__ = ("block", "layout", "d_cap", "P", "K", "H", "W", "num_rendered", "scratch", "settings_keep",
+                 "forward_only")
 
     def view(self, off: int, nbytes: int, dtype) -> torch.Tensor:
         return self.block[off:off + nbytes].view(dtype)
@@ -175,9 +177,10 @@ class _ForwardCall:
     workspace (nothing can have observed the outputs yet)."""
 
     def __init__(self, rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0,
-                 tanfov_dev=None):
+                 tanfov_dev=None, forward_only: bool = False):
         self.raw = raw
         self.tanfov_dev = tanfov_dev
+        self.forward_only = bool(forward_only)    # no backward will follow: no hit records, shorter saved block
         self.args = (means3D, shs, colors, opacities, scales, rotations, cov3D)
         device = means3D.device
         if device.type != "cuda":
@@ -199,7 +202,7 @@ class _ForwardCall:
             if self.stream is None:
                 self.stream = torch.cuda.current_stream(device)
                 self.ws = _workspace(device)
-                self.s, self.keep = _make_settings(self.rs, device, self.raw, self.tanfov_dev)
+                self.s, self.keep = _make_settings(self.rs, device, self.raw, self.tanfov_dev, self.forward_only)
                 if self.out is not None:
                     self.color, self.radii, self.depth, self.alpha = self.out   # caller-owned contiguous slices
                 else:
@@ -223,7 +226,8 @@ class _ForwardCall:
             self.d_cap = ws.capacity_for(P)
             self.L = _lib.layout(P, H, W, self.d_cap)
             self.scratch = ws.ensure_scratch(self.L.scratch_bytes)
-            self.block = torch.empty(self.L.saved_bytes, dtype=torch.uint8, device=device)
+            self.block = torch.empty(self.L.saved_bytes_forward_only if self.forward_only else self.L.saved_bytes,
+                                     dtype=torch.uint8, device=device)
             rc = lib.gsb_forward(C.byref(self.s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
                                  _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), self.radii.data_ptr(),
                                  self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
@@ -246,6 +250,7 @@ class _ForwardCall:
         sv = _Saved()
         sv.block, sv.layout, sv.d_cap, sv.P, sv.K, sv.H, sv.W = self.block, self.L, self.d_cap, self.P, self.K, self.H, self.W
         sv.num_rendered, sv.scratch, sv.settings_keep = D, self.scratch, self.keep
+        sv.forward_only = self.forward_only
         return sv
 
     def finish(self):
@@ -356,9 +361,9 @@ def _active_speculation():
 
 
 def _forward_impl(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out=None, raw: int = 0,
-                  tanfov_dev=None):
+                  tanfov_dev=None, forward_only: bool = False):
     return _ForwardCall(rs, means3D, shs, colors, opacities, scales, rotations, cov3D, out, raw,
-                        tanfov_dev).enqueue().finish()
+                        tanfov_dev, forward_only).enqueue().finish()
 
 
 # Side streams for the batched multi-view entry: the binning stages of a 1-2 M instance view are
@@ -374,13 +379,16 @@ def stats() -> dict:
     return dict(_stats)
 
 
+BLEND_VARIANTS = {"native": 0, "standin": 1, "packed_bwd": 2, "rescan_bwd": 3, "rescan_packed_bwd": 4}
+
+
 def set_blend_variant(name: str) -> None:
-    """'native' (default, the product kernels), 'standin' (reference-STRUCTURE blend kernels of
-    csrc/standin.cu, for measurement context and GPU cross-checks only) or 'packed_bwd' (EXPERIMENTAL
-    backward with a packed shared-memory reduction instead of the per-hit butterfly; parity-checked on
-    one scene only, not benchmarked — DESIGN.md §8.1)."""
-    _lib.check(_lib.load().gsb_set_blend_variant({"native": 0, "standin": 1, "packed_bwd": 2}[name]),
-               "gsb_set_blend_variant")
+    """'native' (default, the product kernels: the forward blend records per-warp hit lists, the backward replays
+    them), 'standin' (reference-STRUCTURE blend kernels of csrc/standin.cu, for measurement context and GPU
+    cross-checks only), 'packed_bwd' (replay backward with a packed shared-memory reduction instead of the per-hit
+    butterfly), 'rescan_bwd' (the record-free round-1 backward that re-walks the tile lists; cross-check of the replay
+    kernel) or 'rescan_packed_bwd'."""
+    _lib.check(_lib.load().gsb_set_blend_variant(BLEND_VARIANTS[name]), "gsb_set_blend_variant")
 
 
 def set_multistream(enabled: bool) -> None:
@@ -567,7 +575,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = _prepare_inputs(
             means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         color, radii, depth, alpha, sv = _forward_impl(raster_settings, means3D, sh, colors_precomp, opacities,
-                                                       scales, rotations, cov3Ds_precomp)
+                                                       scales, rotations, cov3Ds_precomp,
+                                                       forward_only=not any(ctx.needs_input_grad))
         ctx.raster_settings = raster_settings
         ctx.sv = sv
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,
@@ -615,6 +624,7 @@ class _RasterizeViews(torch.autograd.Function):
             raw &= ~(_lib.RAW_SCALE | _lib.RAW_ROTATION)
             ctx.raw = raw
         V = len(settings_list)
+        fo = not any(ctx.needs_input_grad)          # inference: no hit records, shorter saved blocks
         if V == 0:
             raise ValueError("no views")
         H, W = int(settings_list[0].image_height), int(settings_list[0].image_width)
@@ -643,7 +653,7 @@ class _RasterizeViews(torch.autograd.Function):
                         calls.append(_ForwardCall(settings_list[v], means3D, sh, colors_precomp, opacities, scales,
                                                   rotations, cov3Ds_precomp,
                                                   out=(color[v], radii[v], depth[v], alpha[v]), raw=raw,
-                                                  tanfov_dev=tf(v)).enqueue())
+                                                  tanfov_dev=tf(v), forward_only=fo).enqueue())
                 for call in calls:
                     svs.append(call.finish()[4])
             for st in set(streams):
@@ -654,7 +664,7 @@ class _RasterizeViews(torch.autograd.Function):
             for v, rs in enumerate(settings_list):
                 _, _, _, _, sv = _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
                                                cov3Ds_precomp, out=(color[v], radii[v], depth[v], alpha[v]), raw=raw,
-                                               tanfov_dev=tf(v))
+                                               tanfov_dev=tf(v), forward_only=fo)
                 svs.append(sv)
         ctx.settings_list, ctx.svs = list(settings_list), svs
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None, rotations is not None,

@@ -54,6 +54,8 @@ typedef struct GsbSettings {
   int32_t prefiltered;       /* accepted for API parity; every call site passes False */
   int32_t debug;             /* !=0: synchronise + check after every kernel */
   int32_t raw_inputs;        /* GSB_RAW_* bits: which inputs are the model's RAW parameters (0 = the reference's contract) */
+  int32_t forward_only;      /* !=0: no backward pass will use `saved` (inference / playback): the forward blend skips
+                                the hit records and `saved` may be saved_bytes_forward_only bytes long */
   const float* bg;           /* [3]  device */
   const float* viewmatrix;   /* [16] device, column-major world->view (row-vector convention) */
   const float* projmatrix;   /* [16] device, column-major full projection */
@@ -76,6 +78,14 @@ typedef struct GsbLayout {
   size_t off_n_contrib;   /* H*W x u32 */
   size_t off_final_T;     /* H*W x f32 */
   size_t off_tile_order;  /* T x u32  tile ids, heaviest first (CTA scheduling order of the blend kernels) */
+  size_t off_hit_count;   /* T x 8 x u32  hit records written by each of the 8 warps of a tile's CTA (forward blend) */
+  size_t off_hits;        /* 8 x D_cap x {u32 Gaussian id, u32 lane mask}: per (tile, warp) the Gaussians the warp
+                             BLENDED, in list order, with the mask of its 32 pixels that blended them; warp w of the
+                             tile with range [s, e) owns records [8 s + w (e - s), +(e - s)).  Written by the forward
+                             blend, replayed back to front by the backward blend (no culling / alpha tests there).
+                             LAST in the block: a forward that no backward follows (GsbSettings.forward_only) needs
+                             only the first saved_bytes_forward_only bytes */
+  size_t saved_bytes_forward_only;
   size_t scratch_bytes;
   size_t off_rect;        /* P x {u16 minx,miny,maxx,maxy} */
   size_t off_tiles;       /* P x u32  tiles_touched */
@@ -141,7 +151,9 @@ int gsb_read_counts(const void* saved, int P, int H, int W, long long D_cap,
                     uint32_t* host_dst, void* stream);
 
 /* Backward stage 1 — replaces renderCUDA (backward): per-pixel reverse blend, gradients
- * reduced across each warp before one atomic per (warp, Gaussian, component). */
+ * reduced across each warp before one atomic per (warp, Gaussian, component).  Default: replays the hit
+ * records the forward blend wrote into `saved` (see GsbLayout.off_hits); gsb_set_blend_variant selects the
+ * record-free kernel that re-walks the tile lists instead. */
 int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch, long long D_cap,
                    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                    void* stream);
@@ -265,11 +277,14 @@ int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, c
                     long long n_rows, const int64_t* index, long long dst_row0, void* stream);
 
 /* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
- *   0  native kernels (the product path);
+ *   0  native kernels (the product path): forward blend records per-warp hit lists, backward blend replays them;
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
  *      culling, per-pixel global atomics — for measurement context and as a GPU cross-check only;
- *   2  EXPERIMENTAL: native forward + backward with a packed shared-memory reduction instead of the per-hit
- *      shuffle butterfly (csrc/render_bwd.cu, PACKED); parity-checked on one scene only, not benchmarked. */
+ *   2  native forward + replay backward with a packed shared-memory reduction instead of the per-hit shuffle
+ *      butterfly (csrc/render_bwd.cu, PACKED);
+ *   3  native forward + the record-free backward that re-walks the tile lists with per-warp culling (the
+ *      round-1 kernel; cross-check of the replay kernel);
+ *   4  as 3 with the packed reduction. */
 int gsb_set_blend_variant(int variant);
 
 /* Test / measurement helpers. */

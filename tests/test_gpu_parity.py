@@ -50,11 +50,20 @@ def _grad_close(name, got, ref, rtol=GRAD_RTOL):
 # exp; the rounding error scales with the magnitude of the TERMS, not of the possibly cancelled sum, and the mean
 # |gradient| of the tensor is the natural size of such a sum.  Why the mean and not the max: the max-norm bar lets an
 # entry 1000x below the maximum be 10 % wrong; against the mean an entry of typical size must be right to 1e-4 and
-# one 100x below typical to 1 %.
-ATOL_MEAN = 1e-4
+# one 100x below typical to 1 %.  Measured on the B200 (gpurun_out/parity_report.json, "atol_needed_in_units_of_mean"):
+# <= 7e-5 on every regular scene up to 1 M / 3 M Gaussians, so the default is 2e-4 (atomic order varies from run to
+# run).  Two stress scenes need more because their splats are blown up until every Gaussian covers hundreds of pixels
+# and thousands of instances share a tile: a position gradient there sums 1e3-1e4 signed pixel terms that cancel to a
+# few percent of their magnitude (big_splats 2.3e-4, dense_long_lists 2.7e-3 measured); they get their own constants.
+ATOL_MEAN = 2e-4
+ATOL_MEAN_SCENE = {"big_splats": 1e-3, "dense_long_lists": None}
+# dense_long_lists (12 k splats blown up 3x on a 64^2 image, several thousand instances per tile): measured need up
+# to 1.1e-2 x mean, which is the size of the max-norm bar itself (1e-4 x max = 1.7e-2 x mean there), so the
+# per-element bar would add nothing: that scene is held to the max-norm bar only and its statistics are reported.
 
 
-def _grad_close_elementwise(case, name, got, ref, rtol=GRAD_RTOL, atol_mean=ATOL_MEAN):
+def _grad_close_elementwise(case, name, got, ref, rtol=GRAD_RTOL, atol_mean=None):
+    atol_mean = ATOL_MEAN_SCENE.get(case, ATOL_MEAN) if atol_mean is None else atol_mean
     got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
     nz = ref != 0
     mean = ref[nz].abs().mean().item() if bool(nz.any()) else 0.0
@@ -66,6 +75,8 @@ def _grad_close_elementwise(case, name, got, ref, rtol=GRAD_RTOL, atol_mean=ATOL
         "max_abs_err": err.max().item(), "max_abs_ref": ref.abs().max().item(), "mean_abs_ref": mean,
         "atol_needed_in_units_of_mean": need, "fraction_outside_pure_1e-4_relative": pure_rel_viol,
         "wrong_zero_pattern": int(((ref == 0) & (got != 0)).sum().item())}
+    if atol_mean is None:
+        return
     bad = excess > atol_mean * mean
     assert not bool(bad.any()), (f"{case}/{name}: {int(bad.sum())} entries outside 1e-4 |ref| + {atol_mean:g} mean|ref| "
                                  f"(needs {need:.3g} x mean)")
@@ -505,16 +516,19 @@ def test_fused_activations_equal_torch_getters(cuda_device, deg, multistream):
     _grad_close("viewspace", vb, va)
 
 
-@pytest.mark.skipif(os.environ.get("GSB_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variant, only sh0_small has been run on hardware (set GSB_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("name", ["sh0_small", "big_splats", "dense_long_lists", "sh3"])
-def test_experimental_packed_backward_tolerance(cuda_device, name):
-    """The packed-reduction backward (gsb_set_blend_variant(2)) must meet the same gradient bar as the default."""
+@pytest.mark.parametrize("variant", ["packed_bwd", "rescan_bwd", "rescan_packed_bwd"])
+@pytest.mark.parametrize("name", list(SCENES))
+def test_backward_variants_meet_the_same_bar(cuda_device, name, variant):
+    """The default backward blend REPLAYS the hit records the forward wrote; 'rescan_bwd' is the record-free
+    kernel that re-walks the tile lists with per-warp culling (round 1), 'packed_*' reduce through a packed
+    shared-memory slab instead of the shuffle butterfly.  All of them must meet the oracle bar, and — being the same
+    arithmetic over the same (pixel, Gaussian) pairs — agree with the default kernel to summation order."""
     from gaussianip_b200 import rasterizer as R
     scene = util.humanoid_scene(**SCENES[name])
     w = util.loss_weights(scene.H, scene.W)
     ref = util.run_oracle(scene, grads=w, requires_grad=True)
-    R.set_blend_variant("packed_bwd")
+    native = util.run_gpu(scene, cuda_device, grads=w, requires_grad=True, debug=True)
+    R.set_blend_variant(variant)
     try:
         got = util.run_gpu(scene, cuda_device, grads=w, requires_grad=True, debug=True)
     finally:
@@ -522,3 +536,59 @@ def test_experimental_packed_backward_tolerance(cuda_device, name):
     for k, rg in ref["grads"].items():
         if rg is not None:
             _grad_close(k, got["grads"][k], rg)
+            _grad_close_elementwise(name, f"{k}[{variant}]", got["grads"][k], rg)
+            _grad_close(k, got["grads"][k], native["grads"][k], rtol=2e-5)
+
+
+def test_hit_records_are_the_blended_pairs(cuda_device):
+    """The forward's per-warp hit records (GsbLayout.off_hits): per warp an ordered list of {Gaussian id, lane mask};
+    summed over warps, the mask bits of a pixel count exactly the Gaussians it blended, the ids of a warp's records
+    follow the tile's list order, and a pixel's LAST record is its n_contrib-th instance."""
+    scene = util.humanoid_scene(P=4000, H=96, W=112, sh_degree=0, scale_boost=2.0)
+    ref = util.run_oracle(scene)
+    color, radii, depth, alpha, sv, keys = _gpu_forward_state(scene, cuda_device, "two_level")
+    L, T = sv.layout, sv.ranges().shape[0]
+    gx = (scene.W + 15) // 16
+    counts = sv.view(L.off_hit_count, T * 8 * 4, torch.int32).view(T, 8).cpu().numpy()
+    ranges = sv.ranges().cpu().numpy().astype(np.int64)
+    pl = sv.point_list().cpu().numpy().astype(np.int64)
+    D = sv.num_rendered
+    hits = sv.view(L.off_hits, D * 8 * 8, torch.int32).view(D * 8, 2).cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    nc = sv.n_contrib().cpu().numpy()
+    blended = np.zeros((scene.H, scene.W), dtype=np.int64)
+    last_for_pixel = np.zeros((scene.H, scene.W), dtype=np.int64)
+    total = 0
+    for t in range(T):
+        s, e = ranges[t]
+        n = e - s
+        pos_of = {}
+        for j in range(n):
+            pos_of.setdefault(int(pl[s + j]), []).append(j)
+        for wi in range(8):
+            c = counts[t, wi]
+            assert 0 <= c <= n
+            rec = hits[8 * s + wi * n: 8 * s + wi * n + c]
+            total += c
+            last_pos = -1
+            for gid, mask in rec:
+                assert mask != 0
+                # the record's Gaussian sits in the tile's list, after the previous record's
+                cand = [j for j in pos_of[int(gid)] if j > last_pos]
+                assert cand, "record out of list order"
+                last_pos = cand[0]
+                for lane in range(32):
+                    if (mask >> lane) & 1:
+                        y = (t // gx) * 16 + (wi >> 1) * 4 + (lane >> 3)
+                        x = (t % gx) * 16 + (wi & 1) * 8 + (lane & 7)
+                        assert y < scene.H and x < scene.W
+                        blended[y, x] += 1
+                        last_for_pixel[y, x] = last_pos + 1
+    assert total > 0
+    # every pixel's n_contrib is the list position (1-based) of the last record that names it
+    assert (last_for_pixel == nc).all()
+    # number of blended Gaussians per pixel == what the oracle blended (weights > 0), outside marginal pixels
+    img = ref["image"]
+    ok = ~img.marginal.numpy()
+    assert (nc[ok] == img.n_contrib.numpy()[ok]).all()
+    assert ((blended > 0) == (nc > 0)).all()
+    assert (blended <= nc).all()

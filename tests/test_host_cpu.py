@@ -54,7 +54,7 @@ def test_ctypes_prototypes_match_the_header():
                         "double": C.c_double}[" ".join(a.split()[:-1]).replace("const ", "")]
                 assert t is want, f"{name}: '{a}' vs {t}"
     # struct GsbSettings: 9 x 4-byte scalars, padding to 8, 4 pointers
-    assert C.sizeof(_lib.GsbSettings) == 40 + 5 * C.sizeof(C.c_void_p)       # 9 x 4-byte scalars, padding to 8, 5 pointers
+    assert C.sizeof(_lib.GsbSettings) == 40 + 5 * C.sizeof(C.c_void_p)       # 10 x 4-byte scalars, 5 pointers
     m = re.search(r"typedef struct GsbSettings \{(.*?)\} GsbSettings;", src, flags=re.S)
     fields = re.findall(r"(\w+)\s*(?:,|;)", re.sub(r"\b(int32_t|float|const)\b|\*", " ", m.group(1)))
     assert fields == [f[0] for f in _lib.GsbSettings._fields_], fields
