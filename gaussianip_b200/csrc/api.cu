@@ -371,6 +371,10 @@ int gsb_exchange_config(int world, int rank, long long rows_per_rank, const void
   return set_exchange_peers(world, rank, rows_per_rank, peer_bases);
 }
 
+int gsb_exchange_set_aux(int32_t* radii_max, const float* scalar_in, float* scalar_out) {
+  return set_exchange_aux(radii_max, scalar_in, scalar_out);
+}
+
 int gsb_exchange_gather(const float* local_base, float* multicast_base, int n_segments, const long long* offset_floats,
                         const long long* count_floats, void* stream) {
   if (n_segments < 0 || (n_segments > 0 && (!offset_floats || !count_floats))) return GSB_E_INVALID;

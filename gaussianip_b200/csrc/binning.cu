@@ -298,7 +298,7 @@ tiles_partial_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restr
 // single block: exclusive scan of the per-block sums; publishes D and the overflow flag
 __global__ void __launch_bounds__(RS_THREADS)
 scan_blocksums_kernel(uint32_t* __restrict__ blocksums, int num_blocks, uint32_t* __restrict__ counts,
-                      long long D_cap, int mode) {
+                      long long D_cap, int mode, const uint32_t* __restrict__ flag_word) {
   __shared__ uint32_t s_warp[RS_WARPS];
   unsigned long long carry = 0;
   for (int base = 0; base < num_blocks; base += RS_THREADS) {
@@ -315,7 +315,8 @@ scan_blocksums_kernel(uint32_t* __restrict__ blocksums, int num_blocks, uint32_t
     counts[CNT_OVERFLOW] = D > (unsigned long long)D_cap ? 1u : 0u;
     counts[CNT_VISIBLE] = 0; counts[CNT_MAXTILES] = 0;   // reserved; the whole block is copied to the host
     counts[4] = (uint32_t)mode;
-    counts[5] = 0; counts[6] = 0; counts[7] = 0;
+    counts[CNT_PREFILTER] = *flag_word;     // points culled although the caller declared them prefiltered
+    counts[6] = 0; counts[7] = 0;
   }
 }
 
@@ -471,6 +472,9 @@ int radix_prepare(long long n_cap, int end_bit, void* tmp, cudaStream_t st) {
 }
 
 uint32_t* radix_hist0(void* tmp) { return static_cast<uint32_t*>(tmp); }
+// A spare word of the (zeroed) counter row: preprocess_fwd raises it when GsbSettings.prefiltered is set and a point
+// fails the near-plane test; scan_blocksums publishes it as counts[5].
+uint32_t* radix_flag_word(void* tmp) { return static_cast<uint32_t*>(tmp) + MAX_PASSES * 256 + 255; }
 
 // Stable LSD sort on bits [0,end_bit).  Pass 0 reads (src_keys, src_vals); pass p writes
 // buffer A when p is even and buffer B when p is odd.  src may alias B (never A).  The result
@@ -579,7 +583,7 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     // (2) offsets in that order, D, overflow flag
     tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums);
     GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
-    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode);
+    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode, radix_flag_word(hist));
     GSB_POST_LAUNCH(debug, st, "scan_blocksums_kernel");
     if ((rc = publish())) return rc;
     // (3) emit (tile id, Gaussian id) in (depth, id, tile) order, then stable partition by tile
@@ -610,7 +614,7 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     prof_begin(GSB_STAGE_SCAN_EMIT, st);
     tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums);
     GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
-    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode);
+    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode, radix_flag_word(hist));
     GSB_POST_LAUNCH(debug, st, "scan_blocksums_kernel");
     if ((rc = publish())) return rc;
     const int end_bit = 32 + tile_bits;

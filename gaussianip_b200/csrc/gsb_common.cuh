@@ -34,13 +34,14 @@ struct __align__(16) GGrad {
 };
 static_assert(sizeof(GGrad) == 48, "GGrad must be 48 bytes");
 
-enum Counts { CNT_D = 0, CNT_OVERFLOW = 1, CNT_VISIBLE = 2, CNT_MAXTILES = 3 };
+enum Counts { CNT_D = 0, CNT_OVERFLOW = 1, CNT_VISIBLE = 2, CNT_MAXTILES = 3, CNT_MODE = 4, CNT_PREFILTER = 5 };
 
 struct View {           // settings with device pointers, passed by value to kernels
   int H, W, gx, gy;     // image size, tile grid
   float tanfovx, tanfovy, focal_x, focal_y, scale_mod;
   int sh_degree;
   int raw;              // GSB_RAW_* bits
+  int prefiltered;      // the caller asserts that every point passes the frustum test
   const float* bg;
   const float* view;
   const float* proj;
@@ -56,10 +57,18 @@ inline View make_view(const GsbSettings* s) {
   v.focal_x = (float)v.W / (2.0f * s->tanfovx);
   v.focal_y = (float)v.H / (2.0f * s->tanfovy);
   v.scale_mod = s->scale_modifier; v.sh_degree = s->sh_degree; v.raw = s->raw_inputs;
+  v.prefiltered = s->prefiltered;
   v.bg = s->bg; v.view = s->viewmatrix; v.proj = s->projmatrix; v.campos = s->campos;
   v.tanfov_dev = s->tanfov_dev;
   return v;
 }
+
+// Pixel of a lane inside its warp's 8x4 block (blend kernels, hit-record masks): lanes 0-15 are the LEFT 4x4 pixels,
+// lanes 16-31 the RIGHT 4x4 pixels, row-major inside each half.  The two halves of a warp walk their own hit
+// sequences (a splat of ~3.7 px touches 1.4 of the two 4x4 halves on average, but its evaluation costs a warp
+// instruction either way), so bits 0-15 / 16-31 of a record's mask belong to different streams.
+__device__ __forceinline__ int lane_px(int lane) { return (lane & 3) | ((lane >> 4) << 2); }   // 0..7
+__device__ __forceinline__ int lane_py(int lane) { return (lane >> 2) & 3; }                   // 0..3
 
 // Intrinsics of a view: k[0..3] = tanfovx, tanfovy, focal_x, focal_y.  With GsbSettings.tanfov_dev they are read from
 // device memory (a captured CUDA graph can then be replayed with new cameras) and the focal lengths are formed
@@ -206,6 +215,7 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
                      bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st);
 int radix_prepare(long long n_cap, int end_bit, void* tmp, cudaStream_t st);
 uint32_t* radix_hist0(void* tmp);
+uint32_t* radix_flag_word(void* tmp);
 bool radix_result_in_A(int passes);
 int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void* scratch, const GsbLayout& L,
                              long long D_cap, uint64_t* keys_out, cudaStream_t st);
@@ -216,11 +226,17 @@ struct ExchangePeers {
   int world, rank;
   long long rows_per_rank;
   char* base[GSB_MAX_RANKS];        // base address of every rank's copy of the symmetric buffer, as mapped HERE
+  // optional per-launch extras of the fused exchange (gsb_exchange_set_aux): the MAX over ranks of the per-Gaussian
+  // radii and the SUM over ranks of a scalar (the step's loss) ride in the same kernel, so a step needs no NCCL call
+  int32_t* radii_max;               // [P] in the symmetric buffer (multicast address in mode 2, local copy in mode 3)
+  const float* scalar_in;           // this rank's scalar, device
+  float* scalar_out;                // one float in the symmetric buffer (owned by rank 0 in mode 3)
 };
 struct ExchangeSegments {
   long long off[GSB_EXCHANGE_MAX_SEGMENTS], count[GSB_EXCHANGE_MAX_SEGMENTS];
 };
 int set_exchange_peers(int world, int rank, long long rows_per_rank, const void* const* bases);
+int set_exchange_aux(int32_t* radii_max, const float* scalar_in, float* scalar_out);
 int launch_exchange_gather(const float* local, float* mc, int n_seg, const long long* off, const long long* count,
                            cudaStream_t st);
 // densify/prune data movement (compact.cu)

@@ -73,25 +73,37 @@ struct Accum {            // per-Gaussian gradient sums over the views of one la
 // Adds the contribution of ONE view to the sums in A (Gaussian i is visible in that view).
 // DEG = active SH degree (compile time, so the basis / coefficient loops unroll and the 3(DEG+1)^2
 // SH gradient sums stay in registers); sh = this Gaussian's coefficient row (staged in shared memory).
+// What one view contributes for Gaussian i, as loaded from that view's blocks: the gradient record written by the
+// backward blend, the pre-scaled conic + activated opacity of the forward record, the SH clamp mask.  Loaded one
+// view AHEAD of the arithmetic (the kernel is bound by the latency of these dependent loads, ncu r2d: long
+// scoreboard 4.5 of ~7 stall cycles per issue at 23 % occupancy).
+struct ViewRec {
+  float4 g0, g1, g2, con;
+  uint32_t cl;
+};
+__device__ __forceinline__ void load_view_rec(const BwdView& bv, int i, bool want_clamped, ViewRec& r) {
+  const float4* gp = reinterpret_cast<const float4*>(bv.ggrad + i);
+  r.g0 = gp[0]; r.g1 = gp[1]; r.g2 = gp[2];
+  r.con = reinterpret_cast<const float4*>(bv.geom + i)[1];
+  r.cl = want_clamped ? bv.clamped[i] : 0u;
+}
+
 template <int DEG>
 __device__ __forceinline__ void
 view_contrib(const View& v, int i, const float* sV, const float* sM, const float* sCam, const float* sK,
-             const float* __restrict__ means3D, const float (&sc_act)[3], const float4 q_act,
-             const float* sh, const float* __restrict__ cov3Dp, const Geom* __restrict__ geom,
-             const uint8_t* __restrict__ clamped, const GGrad* __restrict__ ggrad, bool precomp_color,
+             const float px, const float py, const float pz, const float (&sc_act)[3], const float4 q_act,
+             const float* sh, const float* __restrict__ cov3Dp, const ViewRec& rec, bool precomp_color,
              Accum<DEG>& A) {
   constexpr int ncoef = (DEG + 1) * (DEG + 1);
-  const float4* gp = reinterpret_cast<const float4*>(ggrad + i);
-  const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+  const float4 g0 = rec.g0, g1 = rec.g1, g2 = rec.g2;
   // moments -> gradients of the screen-space mean (NDC units) and of the conic
-  float4 con = reinterpret_cast<const float4*>(geom + i)[1];         // pre-scaled conic, opacity
+  float4 con = rec.con;                                              // pre-scaled conic, opacity
   con.x *= 1.0f / CONIC_SCALE_AC; con.y *= 1.0f / CONIC_SCALE_B; con.z *= 1.0f / CONIC_SCALE_AC;   // back to A, B, C
   const float gx = -(con.x * g0.x + con.y * g0.y) * (0.5f * (float)v.W);
   const float gy = -(con.z * g0.y + con.y * g0.x) * (0.5f * (float)v.H);
   const float gA = -0.5f * g0.z, gB = -g0.w, gC = -0.5f * g1.x, gop = g1.y, gdepth = g1.z;
   float grgb[3] = {g1.w, g2.x, g2.y};
 
-  const float px = means3D[3 * i], py = means3D[3 * i + 1], pz = means3D[3 * i + 2];
   const float tx = sV[0] * px + sV[4] * py + sV[8] * pz + sV[12];
   const float ty = sV[1] * px + sV[5] * py + sV[9] * pz + sV[13];
   const float tz = sV[2] * px + sV[6] * py + sV[10] * pz + sV[14];
@@ -101,7 +113,7 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
   if (precomp_color) {
     A.dcol[0] += grgb[0]; A.dcol[1] += grgb[1]; A.dcol[2] += grgb[2];
   } else {
-    const uint8_t cl = clamped[i];
+    const uint32_t cl = rec.cl;
     if (cl & 1) grgb[0] = 0.f;
     if (cl & 2) grgb[1] = 0.f;
     if (cl & 4) grgb[2] = 0.f;
@@ -298,8 +310,11 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
   }
 }
 
+#ifndef GSB_PBWD_MINB
+#define GSB_PBWD_MINB 2
+#endif
 template <int DEG, int MODE>     // MODE 0: store / accumulate locally, 2: multicast red into all copies, 3: red into the owner's copy
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (DEG <= 1 ? GSB_PBWD_MINB : 2))
 preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rots,
                       const float* __restrict__ shs, const float* __restrict__ cov3Dp,
@@ -323,6 +338,7 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   const float* my_sh = shs ? shs + (size_t)i * K * 3 : nullptr;
 
   Accum<DEG> A;
+  int rmax = 0;                      // largest radius of this Gaussian over the views of the launch
 #pragma unroll
   for (int k = 0; k < 3; ++k) { A.dp[k] = 0.f; A.dsc[k] = 0.f; A.dcol[k] = 0.f; }
   A.d2[0] = A.d2[1] = 0.f; A.dop = 0.f;
@@ -344,12 +360,28 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
       q = reinterpret_cast<const float4*>(rots)[i];
       if (raw & GSB_RAW_ROTATION) q = act_normalize(q, &qn);
     }
-    for (int vi = 0; vi < B.V; ++vi) {
-      const BwdView& bv = B.a[vi];
-      if (bv.radii[i] <= 0) continue;       // gradients of culled Gaussians are exactly 0
-      view_contrib<DEG>(bv.v, i, sV[vi], sM[vi], sCam[vi], sK[vi], means3D, sc, q, my_sh, cov3Dp, bv.geom, bv.clamped,
-                        bv.ggrad, dcolors != nullptr, A);
-      o_act = reinterpret_cast<const float4*>(bv.geom + i)[1].w;      // activated opacity, as the forward stored it
+    // radii of all views first (independent loads), then the per-view records one view ahead of the arithmetic
+    const float px = means3D[3 * i], py = means3D[3 * i + 1], pz = means3D[3 * i + 2];
+    uint32_t seen = 0;
+#pragma unroll
+    for (int vi = 0; vi < GSB_MAX_VIEWS; ++vi) {
+      const int rv = vi < B.V ? B.a[vi].radii[i] : 0;
+      if (rv > 0) seen |= 1u << vi;                                 // gradients of culled Gaussians are exactly 0
+      rmax = max(rmax, rv);
+    }
+    const bool want_cl = dcolors == nullptr;
+    ViewRec cur, nxt;
+    int vi = seen ? __ffs(seen) - 1 : -1;
+    if (vi >= 0) load_view_rec(B.a[vi], i, want_cl, cur);
+    while (vi >= 0) {
+      seen &= seen - 1;
+      const int vn = seen ? __ffs(seen) - 1 : -1;
+      if (vn >= 0) load_view_rec(B.a[vn], i, want_cl, nxt);
+      view_contrib<DEG>(B.a[vi].v, i, sV[vi], sM[vi], sCam[vi], sK[vi], px, py, pz, sc, q, my_sh, cov3Dp, cur,
+                        dcolors != nullptr, A);
+      o_act = cur.con.w;                                            // activated opacity, as the forward stored it
+      cur = nxt;
+      vi = vn;
     }
     // chain rule to the RAW parameters, applied once to the sum over views
     if (raw & GSB_RAW_OPACITY) A.dop = A.dop * (1.0f - o_act) * o_act;                    // sigmoid'
@@ -370,7 +402,24 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
     float* stage = s_stage[threadIdx.x >> 5];
     const int first = i - lane;
     const int n_valid = min(32, P - first);
+    // extras riding in the exchange: the step's scalar (one thread of the launch) and the radii maximum
+    if (X.scalar_in && blockIdx.x == 0 && threadIdx.x == 0) {
+      float* dst = X.scalar_out;
+      if (MODE == 3) dst = reinterpret_cast<float*>(reinterpret_cast<char*>(dst) + (X.base[0] - X.base[X.rank]));
+      mc_red<MM>(dst, *X.scalar_in);
+    }
     if (n_valid <= 0) return;               // warp-uniform
+    if (X.radii_max && i < P && rmax > 0) {
+      int32_t* dst = X.radii_max + i;
+      if (MODE == 3) {
+        int owner = (int)(first / X.rows_per_rank);
+        owner = owner < X.world ? owner : X.world - 1;
+        dst = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(dst) + (X.base[owner] - X.base[X.rank]));
+        asm volatile("red.relaxed.sys.global.max.s32 [%0], %1;" ::"l"(dst), "r"(rmax) : "memory");
+      } else {
+        asm volatile("multimem.red.relaxed.sys.global.max.s32 [%0], %1;" ::"l"(dst), "r"(rmax) : "memory");
+      }
+    }
     if (MODE == 3) {
       // this warp's 32 rows belong to one owner (blocks are multiples of 32 rows): retarget every output
       // from the local copy to the same offset inside the owner's copy
@@ -495,7 +544,14 @@ int set_exchange_peers(int world, int rank, long long rows_per_rank, const void*
     if (!bases[r]) return GSB_E_INVALID;
     x.base[r] = static_cast<char*>(const_cast<void*>(bases[r]));
   }
+  x.radii_max = g_peers.radii_max; x.scalar_in = g_peers.scalar_in; x.scalar_out = g_peers.scalar_out;
   g_peers = x;
+  return GSB_OK;
+}
+
+int set_exchange_aux(int32_t* radii_max, const float* scalar_in, float* scalar_out) {
+  if ((scalar_in != nullptr) != (scalar_out != nullptr)) return GSB_E_INVALID;
+  g_peers.radii_max = radii_max; g_peers.scalar_in = scalar_in; g_peers.scalar_out = scalar_out;
   return GSB_OK;
 }
 
@@ -526,6 +582,7 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
   if (P == 0) return GSB_OK;
   if (B.V < 1 || B.V > GSB_MAX_VIEWS) return GSB_E_INVALID;
   if (accumulate == 3 && g_peers.world < 1) return GSB_E_INVALID;     // gsb_exchange_config was not called
+  if (accumulate == 2 && g_peers.world < 1) { g_peers.world = 1; g_peers.rank = 0; g_peers.rows_per_rank = 32; }
   const int deg = B.a[0].v.sh_degree;
   for (int v = 1; v < B.V; ++v)
     if (B.a[v].v.sh_degree != deg) return GSB_E_INVALID;   // one degree per launch

@@ -129,8 +129,8 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   int* seg_start = reinterpret_cast<int*>(slab + SLAB * SLAB_STRIDE);        // [SEG_MAX + 2]
   uint32_t* seg_gid = reinterpret_cast<uint32_t*>(seg_start + SEG_MAX + 2);  // [SEG_MAX]
   int n_pairs = 0, n_seg = 0;                                                // warp-uniform
-  const int pix_x = tx * TILE_X + wx + (lane & 7);
-  const int pix_y = ty * TILE_Y + wy + (lane >> 3);
+  const int pix_x = tx * TILE_X + wx + lane_px(lane);
+  const int pix_y = ty * TILE_Y + wy + lane_py(lane);
   const bool inside = pix_x < v.W && pix_y < v.H;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
   // Cull rectangle of the warp = bounding box of the pixels that have started their walk (a
@@ -213,7 +213,7 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
     const uint32_t active = __ballot_sync(0xffffffffu, started);
     if (active != active_prev) {
       active_prev = active;
-      const int lx = lane & 7, ly = lane >> 3;
+      const int lx = lane_px(lane), ly = lane_py(lane);
       const int x0 = __reduce_min_sync(0xffffffffu, started ? lx : 64), x1 = __reduce_max_sync(0xffffffffu, started ? lx : -1);
       const int y0 = __reduce_min_sync(0xffffffffu, started ? ly : 64), y1 = __reduce_max_sync(0xffffffffu, started ? ly : -1);
       hwx = 0.5f * (float)(x1 - x0); hwy = 0.5f * (float)(y1 - y0);
@@ -341,6 +341,42 @@ render_bwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 // Bdot), same raw-moment outputs; the iteration space is the warp's record list instead of the tile's instance list.
 // Records are fetched 32 at a time (one coalesced 256 B load, lane l <- record l), their Geom rows gathered with
 // cp.async into the same 2-stage ring, one block of records ahead of the arithmetic.
+// The two HALVES of the warp (lanes 0-15 / 16-31 = left / right 4x4 pixels, bits 0-15 / 16-31 of a record's mask)
+// replay their own subsequences of a block: an iteration handles the next record of the left half and the next
+// record of the right half — usually two different Gaussians — and reduces the ten partial sums of each over its
+// 16 lanes with a 12-shuffle butterfly, so a block of 32 records costs max(|A|, |B|) iterations instead of 32.
+
+// Sum 12 per-lane values over the 16 lanes of a half-warp.  On return lane L holds the total of slot
+// (L&8 ? 6:0) + (L&4 ? 3:0) + (L&2 ? 2:0) + (L&1 ? 1:0); the combination (L&2 && L&1) is the padding slot.
+__device__ __forceinline__ float butterfly12_half(const float (&v)[12], int lane) {
+  const bool b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+  float u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float keep = b3 ? v[i + 6] : v[i];
+    const float send = b3 ? v[i] : v[i + 6];
+    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float t[4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float keep = b2 ? u[i + 3] : u[i];
+    const float send = b2 ? u[i] : u[i + 3];
+    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  t[3] = 0.0f;
+  float s[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = b1 ? t[i + 2] : t[i];
+    const float send = b1 ? t[i] : t[i + 2];
+    s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float keep = b0 ? s[1] : s[0];
+  const float send = b0 ? s[0] : s[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 template <bool PACKED>
 __global__ void __launch_bounds__(WARPS * 32)
 render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __restrict__ ranges,
@@ -356,6 +392,7 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
   const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4;
   const int n_rec = (int)hit_count[tile * WARPS + warp];
   if (n_rec == 0) return;
   const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
@@ -363,8 +400,8 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
   int* seg_start = reinterpret_cast<int*>(slab + SLAB * SLAB_STRIDE);        // [SEG_MAX + 2]
   uint32_t* seg_gid = reinterpret_cast<uint32_t*>(seg_start + SEG_MAX + 2);  // [SEG_MAX]
   int n_pairs = 0, n_seg = 0;                                                // warp-uniform
-  const int pix_x = tx * TILE_X + wx + (lane & 7);
-  const int pix_y = ty * TILE_Y + wy + (lane >> 3);
+  const int pix_x = tx * TILE_X + wx + lane_px(lane);
+  const int pix_y = ty * TILE_Y + wy + lane_py(lane);
   const bool inside = pix_x < v.W && pix_y < v.H;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
   const size_t hw = (size_t)v.H * v.W;
@@ -398,8 +435,8 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
         cp_async16(&st[0][lane], src);
         cp_async16(&st[1][lane], src + 1);
         cp_async16(&st[2][lane], src + 2);
-        mring[c & (STAGES - 1)][lane] = rec;
       }
+      mring[c & (STAGES - 1)][lane] = rec;        // (0, 0) beyond the end: belongs to neither half
     }
     cp_async_commit();
   };
@@ -423,8 +460,8 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
   for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_rec(c));
   uint2 rec_next = fetch_rec(STAGES - 1);
 
-  const int slot = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-  const bool writer = !(lane & 1) && !((lane & 4) && (lane & 2)) && slot < 10;
+  const int slot = ((lane & 8) ? 6 : 0) + ((lane & 4) ? 3 : 0) + ((lane & 2) ? 2 : 0) + ((lane & 1) ? 1 : 0);
+  const bool writer = !((lane & 2) && (lane & 1)) && slot < 10;
   for (int c = 0; c < blocks; ++c) {
     issue(c + STAGES - 1, rec_next);
     rec_next = fetch_rec(c + STAGES);
@@ -432,79 +469,80 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
     __syncwarp();
     float4 (*st)[32] = ring[c & (STAGES - 1)];
     const uint2* meta = mring[c & (STAGES - 1)];
-    const int base = (blocks - 1 - c) * 32;
-    const int nb = min(32, n_rec - base);
-    // RB records at a time: their loads, Gaussian weights and 13-shuffle reductions are independent and overlap;
-    // only the short transmittance / suffix-sum chain runs in order.  The replay kernel is bound by its longest
-    // warps (a heavy tile's warp replays ~1e3 records one after the other), so the latency of one record's chain
-    // matters more than registers here.
-    for (int r = nb - 1; r >= 0; r -= RB) {
-      uint2 mr[RB];
-      bool valid[RB];
-      float dx[RB], dy[RB], G[RB], alpha[RB];
-      float4 q[RB], f[RB];
+    // which records of this block concern the left / the right half
+    const uint32_t mine = meta[lane].y;
+    const uint32_t recsA = __ballot_sync(0xffffffffu, (mine & 0x0000ffffu) != 0u);
+    const uint32_t recsB = __ballot_sync(0xffffffffu, (mine & 0xffff0000u) != 0u);
+    uint32_t pend = half ? recsB : recsA;         // every lane keeps the pending records of ITS half
+    while (__any_sync(0xffffffffu, pend != 0u)) {
+      // back to front: the highest remaining record of this lane's half (-1: none left)
+      const int r = 31 - __clz(pend);
+      pend &= ~(r >= 0 ? (1u << r) : 0u);
+      uint2 mr = make_uint2(0u, 0u);
+      bool valid = false;
+      float g[12];
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const int ri = r - i;
-        valid[i] = false;
-        mr[i] = make_uint2(0u, 0u);
-        if (ri >= 0) {
-          mr[i] = meta[ri];                               // {Gaussian id, lanes that blended it}: warp-uniform
-          valid[i] = (mr[i].y >> lane) & 1u;
-          const float4 a = st[0][ri];
-          q[i] = st[1][ri];
-          f[i] = st[2][ri];
-          dx[i] = a.x - pxf; dy[i] = a.y - pyf;
-          G[i] = exp2_blend(gauss_exponent2(q[i].x, q[i].y, q[i].z, dx[i], dy[i]));
-          alpha[i] = fminf(ALPHA_CAP, q[i].w * G[i]);
-        }
-      }
-      float g[RB][12];
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) g[i][j] = 0.0f;
-        if (valid[i]) {
-          const float inv1ma = rcp_blend(1.0f - alpha[i]);
+      for (int j = 0; j < 12; ++j) g[j] = 0.0f;
+      if (r >= 0) {
+        mr = meta[r];                                     // {Gaussian id, lanes that blended it}: uniform per half
+        valid = (mr.y >> lane) & 1u;
+        if (valid) {
+          const float4 a = st[0][r];
+          const float4 q = st[1][r];
+          const float4 f = st[2][r];
+          const float dx = a.x - pxf, dy = a.y - pyf;
+          const float G = exp2_blend(gauss_exponent2(q.x, q.y, q.z, dx, dy));
+          const float alpha = fminf(ALPHA_CAP, q.w * G);
+          // With phi_j = <c_j, dL/dC> + depth_j dL/dD + dL/dA and the suffix sum
+          //   Bdot_i = T_final <bg, dL/dC> + sum_{j behind i} phi_j alpha_j T_j,
+          // dL/dalpha_i = T_i phi_i - Bdot_i / (1 - alpha_i)
+          const float inv1ma = rcp_blend(1.0f - alpha);
           T *= inv1ma;
-          const float w = alpha[i] * T;
-          const float phi = f[i].y * gC0 + f[i].z * gC1 + f[i].w * gC2 + f[i].x * gD + gA;
+          const float w = alpha * T;
+          const float phi = f.y * gC0 + f.z * gC1 + f.w * gC2 + f.x * gD + gA;
           const float dL_da = T * phi - Bdot * inv1ma;
           Bdot += phi * w;
-          const float s_ = q[i].w * dL_da * G[i];
-          g[i][0] = s_ * dx[i];
-          g[i][1] = s_ * dy[i];
-          g[i][2] = g[i][0] * dx[i];
-          g[i][3] = g[i][0] * dy[i];
-          g[i][4] = g[i][1] * dy[i];
-          g[i][5] = G[i] * dL_da;
-          g[i][6] = w * gD;
-          g[i][7] = w * gC0;
-          g[i][8] = w * gC1;
-          g[i][9] = w * gC2;
+          // raw moments of s = dL/dG * G about the splat centre; the linear maps to d(ndc xy) and d(conic)
+          // are applied once per Gaussian in preprocess_bwd
+          const float s_ = q.w * dL_da * G;
+          g[0] = s_ * dx;
+          g[1] = s_ * dy;
+          g[2] = g[0] * dx;
+          g[3] = g[0] * dy;
+          g[4] = g[1] * dy;
+          g[5] = G * dL_da;
+          g[6] = w * gD;
+          g[7] = w * gC0;
+          g[8] = w * gC1;
+          g[9] = w * gC2;
         }
       }
+      if (PACKED) {
+        // one segment per (half, record): the left half's first, then the right half's
+        const int rA = __shfl_sync(0xffffffffu, r, 0), rB = __shfl_sync(0xffffffffu, r, 16);
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        if (r - i < 0) continue;
-        if (PACKED) {
-          const int nv = __popc(mr[i].y);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int rr = hh ? rB : rA;
+          if (rr < 0) continue;
+          const uint2 m2 = meta[rr];
+          const uint32_t bits = m2.y & (hh ? 0xffff0000u : 0x0000ffffu);
+          const int nv = __popc(bits);
           if (n_pairs + nv > SLAB || n_seg == SEG_MAX) flush();
-          if (lane == 0) { seg_start[n_seg] = n_pairs; seg_gid[n_seg] = mr[i].x; }
-          if (valid[i]) {
-            float* dst = slab + (n_pairs + __popc(mr[i].y & ((1u << lane) - 1u))) * SLAB_STRIDE;
+          if (lane == 0) { seg_start[n_seg] = n_pairs; seg_gid[n_seg] = m2.x; }
+          if (half == hh && valid) {
+            float* dst = slab + (n_pairs + __popc(bits & ((1u << lane) - 1u))) * SLAB_STRIDE;
 #pragma unroll
-            for (int j = 0; j < 10; ++j) dst[j] = g[i][j];
+            for (int j = 0; j < 10; ++j) dst[j] = g[j];
           }
           n_pairs += nv; ++n_seg;
-        } else {
-          const float tot = butterfly12(g[i], lane);
-#ifdef GSB_BWD_NO_RED      // diagnostic build only (timing without the global reductions; results are wrong)
-          if (writer && tot == 123.456f) atomicAdd(reinterpret_cast<float*>(ggrad + mr[i].x) + slot, tot);
-#else
-          if (writer && tot != 0.0f) atomicAdd(reinterpret_cast<float*>(ggrad + mr[i].x) + slot, tot);
-#endif
         }
+      } else {
+        const float tot = butterfly12_half(g, lane);
+#ifdef GSB_BWD_NO_RED      // diagnostic build only (timing without the global reductions; results are wrong)
+        if (r >= 0 && writer && tot == 123.456f) atomicAdd(reinterpret_cast<float*>(ggrad + mr.x) + slot, tot);
+#else
+        if (r >= 0 && writer && tot != 0.0f) atomicAdd(reinterpret_cast<float*>(ggrad + mr.x) + slot, tot);
+#endif
       }
     }
     __syncwarp();

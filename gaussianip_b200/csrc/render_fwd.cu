@@ -1,8 +1,10 @@
 // Stage 3: per-tile front-to-back alpha blending.  Replaces renderCUDA (forward) of the
 // external operator ("Forward blend").
 //
-// One CTA per 16x16 tile, 8 warps; warp w owns an 8x4 pixel block so that a small splat
-// overlaps few warps.  The warps of a CTA are fully INDEPENDENT (no __syncthreads): each walks
+// One CTA per 16x16 tile, 8 warps; warp w owns an 8x4 pixel block, and inside the warp lanes 0-15 / 16-31 own its
+// left / right 4x4 pixels (lane_px / lane_py).  The two HALVES take their own hits: a ~3.7 px splat overlaps 1.4
+// of the two 4x4 blocks on average, so letting each half evaluate a different Gaussian in the same instruction
+// stream cuts the evaluation iterations of a chunk from |hits(A) u hits(B)| to max(|hits(A)|, |hits(B)|).  The warps of a CTA are fully INDEPENDENT (no __syncthreads): each walks
 // the tile's sorted instance list in chunks of 32, gathering point_list -> 48 B Geom record
 // (L2-resident) into its own shared-memory ring with cp.async, STAGES chunks ahead of the
 // blend.  Lane l first tests whether instance l of the chunk can reach any of the warp's 32
@@ -55,22 +57,25 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
                   uint2* __restrict__ hits, uint32_t* __restrict__ hit_count) {
   extern __shared__ float4 smem_dyn[];             // 12 KB per stage per CTA
   float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
-  // RECORD: per warp, the blend masks of the current chunk's 32 instances
-  uint32_t (*s_mask)[32] = reinterpret_cast<uint32_t (*)[32]>(smem_dyn + WARPS * STAGES * 3 * 32);
+  // RECORD: per warp and half, the blend masks of the current chunk's 32 instances
+  uint32_t (*s_mask)[2][32] = reinterpret_cast<uint32_t (*)[2][32]>(smem_dyn + WARPS * STAGES * 3 * 32);
 
   const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4;                      // 0: left 4x4 pixels of the warp's 8x4 block, 1: right 4x4
   const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
-  const int pix_x = tx * TILE_X + wx + (lane & 7);
-  const int pix_y = ty * TILE_Y + wy + (lane >> 3);
+  const int lx = lane_px(lane), ly = lane_py(lane);
+  const int pix_x = tx * TILE_X + wx + lx;
+  const int pix_y = ty * TILE_Y + wy + ly;
   const bool inside = pix_x < v.W && pix_y < v.H;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
-  // Cull rectangle of the warp = bounding box of its pixels that are still accumulating.  It
-  // starts as the whole 8x4 block and shrinks as pixels saturate, so the long-running warps
-  // (a few unsaturated silhouette pixels) stop paying for splats that only reach finished pixels.
-  float cxw = (float)(tx * TILE_X + wx) + 3.5f, cyw = (float)(ty * TILE_Y + wy) + 1.5f;
-  float hwx = 3.5f, hwy = 1.5f;
+  // Cull rectangles, one per half = bounding box of the half's pixels that are still accumulating.  They start as
+  // the whole 4x4 blocks and shrink as pixels saturate, so the long-running warps (a few unsaturated silhouette
+  // pixels) stop paying for splats that only reach finished pixels.  Every lane keeps both: lane l tests
+  // instance l of a chunk against the two halves.
+  float cxA = (float)(tx * TILE_X + wx) + 1.5f, cxB = cxA + 4.0f, cyA = (float)(ty * TILE_Y + wy) + 1.5f, cyB = cyA;
+  float hwxA = 1.5f, hwyA = 1.5f, hwxB = 1.5f, hwyB = 1.5f;
   uint32_t alive_prev = 0xffffffffu;
 
   const uint2 range = ranges[tile];
@@ -117,7 +122,7 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       const uint32_t gid_issued = gid_next;
       issue(c + STAGES - 1, gid_next);
       gid_next = fetch_gid(c + STAGES);
-      if (RECORD) s_mask[warp][lane] = 0u;
+      if (RECORD) { s_mask[warp][0][lane] = 0u; s_mask[warp][1][lane] = 0u; }
       cp_async_wait<STAGES - 1>();               // chunk c has landed (for this lane)
       __syncwarp();                              // ... and for every lane of the warp
       float4 (*st)[32] = ring[c & (STAGES - 1)];
@@ -125,27 +130,46 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       const bool done = T == 0.0f;
       const uint32_t alive = __ballot_sync(0xffffffffu, !done);
       if (alive != alive_prev) {
+        const uint32_t changed = alive ^ alive_prev;
         alive_prev = alive;
-        const int lx = lane & 7, ly = lane >> 3;
-        const int x0 = __reduce_min_sync(0xffffffffu, done ? 64 : lx), x1 = __reduce_max_sync(0xffffffffu, done ? -1 : lx);
-        const int y0 = __reduce_min_sync(0xffffffffu, done ? 64 : ly), y1 = __reduce_max_sync(0xffffffffu, done ? -1 : ly);
-        hwx = 0.5f * (float)(x1 - x0); hwy = 0.5f * (float)(y1 - y0);
-        cxw = (float)(tx * TILE_X + wx + x0) + hwx; cyw = (float)(ty * TILE_Y + wy + y0) + hwy;
+        const int hx = lane & 3;                 // x inside the half
+        if (changed & 0x0000ffffu) {
+          const bool on = !done && half == 0;
+          const int x0 = __reduce_min_sync(0xffffffffu, on ? hx : 64), x1 = __reduce_max_sync(0xffffffffu, on ? hx : -1);
+          const int y0 = __reduce_min_sync(0xffffffffu, on ? ly : 64), y1 = __reduce_max_sync(0xffffffffu, on ? ly : -1);
+          hwxA = 0.5f * (float)(x1 - x0); hwyA = 0.5f * (float)(y1 - y0);
+          cxA = (float)(tx * TILE_X + wx + x0) + hwxA; cyA = (float)(ty * TILE_Y + wy + y0) + hwyA;
+        }
+        if (changed & 0xffff0000u) {
+          const bool on = !done && half == 1;
+          const int x0 = __reduce_min_sync(0xffffffffu, on ? hx : 64), x1 = __reduce_max_sync(0xffffffffu, on ? hx : -1);
+          const int y0 = __reduce_min_sync(0xffffffffu, on ? ly : 64), y1 = __reduce_max_sync(0xffffffffu, on ? ly : -1);
+          hwxB = 0.5f * (float)(x1 - x0); hwyB = 0.5f * (float)(y1 - y0);
+          cxB = (float)(tx * TILE_X + wx + 4 + x0) + hwxB; cyB = (float)(ty * TILE_Y + wy + y0) + hwyB;
+        }
       }
-      bool hit = false;
+      bool hitA = false, hitB = false;
       if (e < n) {
         const float4 a = st[0][lane];
-        hit = (fabsf(a.x - cxw) <= a.z + hwx) && (fabsf(a.y - cyw) <= a.w + hwy);
+        hitA = (fabsf(a.x - cxA) <= a.z + hwxA) && (fabsf(a.y - cyA) <= a.w + hwyA);
+        hitB = (fabsf(a.x - cxB) <= a.z + hwxB) && (fabsf(a.y - cyB) <= a.w + hwyB);
       }
-      uint32_t mask = __ballot_sync(0xffffffffu, hit);
-      // Hits are taken HB (= 2) at a time: their alphas (LDS, conic, ex2) are independent and overlap;
-      // only the short transmittance chain is applied in order (4 at a time measured slower: registers).
-      while (mask) {
+      // a half without live pixels takes no hits (its rectangle is empty: negative half-widths can still pass
+      // the test for degenerate splats of infinite extent)
+      // every lane keeps the pending hits of ITS half (a half without live pixels takes none: its rectangle is
+      // empty, but negative half-widths can still pass the test for degenerate splats of infinite extent)
+      const uint32_t maskA = __ballot_sync(0xffffffffu, hitA), maskB = __ballot_sync(0xffffffffu, hitB);
+      uint32_t pend = half ? maskB : maskA;
+      if (!(alive & (half ? 0xffff0000u : 0x0000ffffu))) pend = 0u;
+      // The two halves take their own hits, in list order, HB at a time each: an iteration evaluates up to
+      // 2 x HB (half, Gaussian) pairs with one warp instruction stream.  Alphas (LDS, conic, ex2) of the HB hits
+      // are independent and overlap; only the short transmittance chain is applied in order.
+      while (__any_sync(0xffffffffu, pend != 0u)) {
         int k[HB];
 #pragma unroll
         for (int i = 0; i < HB; ++i) {
-          k[i] = mask ? __ffs(mask) - 1 : -1;
-          mask &= mask - 1;
+          k[i] = __ffs(pend) - 1;               // -1 when this half has no hit left
+          pend &= pend - 1;
         }
         float al[HB];
         float4 ff[HB];
@@ -177,15 +201,16 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
             T = ok ? test_T : 0.0f;       // a saturating splat (or a finished pixel) leaves T at 0
           }
           if (RECORD) {
-            const uint32_t vb = __ballot_sync(0xffffffffu, ok);     // the pixels that blended this Gaussian
-            if (lane == 0 && k[i] >= 0) s_mask[warp][k[i]] = vb;
+            // bits 0-15: the left pixels that blended the left half's Gaussian; bits 16-31: the right half's
+            const uint32_t vb = __ballot_sync(0xffffffffu, ok);
+            if ((lane & 15) == 0 && k[i] >= 0) s_mask[warp][half][k[i]] = half ? (vb & 0xffff0000u) : (vb & 0x0000ffffu);
           }
         }
       }
       if (RECORD) {
-        // append this chunk's records: instance l of the chunk was blended by the pixels in s_mask[l]
+        // append this chunk's records: instance l of the chunk was blended by the pixels in its two masks
         __syncwarp();
-        const uint32_t m = s_mask[warp][lane];
+        const uint32_t m = s_mask[warp][0][lane] | s_mask[warp][1][lane];
         const uint32_t nz = __ballot_sync(0xffffffffu, m != 0u);
         if (m) rec_base[rec_n + __popc(nz & ((1u << lane) - 1u))] = make_uint2(gid_cur, m);
         rec_n += __popc(nz);
@@ -223,7 +248,7 @@ int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_lis
 #ifndef GSB_FWD_SMEM_PAD
 #define GSB_FWD_SMEM_PAD 0
 #endif
-  constexpr size_t smem = (size_t)WARPS * STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint32_t)) + GSB_FWD_SMEM_PAD;
+  constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4) + (size_t)WARPS * 2 * 32 * sizeof(uint32_t) + GSB_FWD_SMEM_PAD;
   static std::atomic<unsigned long long> configured{0};   // bit per device: the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));

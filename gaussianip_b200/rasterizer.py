@@ -236,6 +236,8 @@ class _ForwardCall:
             _lib.check(rc, "gsb_forward")
         return self
 
+    PREFILTER_MSG = "Point is filtered although prefiltered is set. This shouldn't happen!"
+
     def _account(self, D: int) -> None:
         ws, P = self.ws, self.P
         ws.last_num_rendered = D
@@ -268,6 +270,8 @@ class _ForwardCall:
         while True:
             ws.event.synchronize()          # waits for the 32-byte counts copy only
             D = int(ws.host_counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
+            if P > 0 and int(ws.host_counts[5].item()):
+                raise RuntimeError(self.PREFILTER_MSG)      # the external operator traps the device here
             if D <= self.d_cap:
                 break
             ws.d_cap = int(D * 1.25) + 4096   # outputs were not observable yet: enqueue again, larger
@@ -285,6 +289,8 @@ class _ForwardCall:
         if self.counts is not None:
             # captured call: the caller has waited for the replay (graph.CapturedStep.validate)
             D = int(self.counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
+            if P > 0 and int(self.counts[5].item()):
+                raise RuntimeError(self.PREFILTER_MSG)
             self.fits = D <= self.d_cap
             if self.fits:
                 self.sv.num_rendered = D
@@ -300,6 +306,8 @@ class _ForwardCall:
         ws.event.synchronize()
         D = int(ws.host_counts[0].item()) & 0xFFFFFFFF if P > 0 else 0
         ws.pending = None
+        if P > 0 and int(ws.host_counts[5].item()):
+            raise RuntimeError(self.PREFILTER_MSG)
         self.fits = D <= self.d_cap
         if self.fits:
             self.sv.num_rendered = D

@@ -51,7 +51,8 @@ typedef struct GsbSettings {
   float tanfovx, tanfovy;
   float scale_modifier;
   int32_t sh_degree;         /* active degree, 0..3 */
-  int32_t prefiltered;       /* accepted for API parity; every call site passes False */
+  int32_t prefiltered;       /* !=0: the caller asserts every point passes the near-plane test; a point that does not
+                                raises counts[5] (the external operator traps the device there); call sites pass False */
   int32_t debug;             /* !=0: synchronise + check after every kernel */
   int32_t raw_inputs;        /* GSB_RAW_* bits: which inputs are the model's RAW parameters (0 = the reference's contract) */
   int32_t forward_only;      /* !=0: no backward pass will use `saved` (inference / playback): the forward blend skips
@@ -72,7 +73,7 @@ typedef struct GsbLayout {
   size_t saved_bytes;
   size_t off_geom;        /* P x 48 B  GsbGeom record {x,y,extx,exty | qa,qb,qc (conic scaled by -0.5log2e,-log2e,-0.5log2e),opacity | depth,r,g,b} */
   size_t off_clamped;     /* P x u8    SH clamp mask (bit c: channel c clamped at 0) */
-  size_t off_counts;      /* 8 x u32   [0]=D (num_rendered) [1]=overflow flag [2]=#visible [3]=max tiles per Gaussian */
+  size_t off_counts;      /* 8 x u32   [0]=D (num_rendered) [1]=overflow flag [4]=binning mode [5]=prefiltered violated */
   size_t off_point_list;  /* D_cap x u32  Gaussian index per sorted instance */
   size_t off_ranges;      /* T x {u32 start,u32 end} */
   size_t off_n_contrib;   /* H*W x u32 */

@@ -391,7 +391,9 @@ def blend_tiles(g: Geom, b: Binning, bg: torch.Tensor, H: int, W: int, chunk: in
                 - (con[:, 1][None, :] * dx) * dy
             G = torch.exp(power)
             a_raw = g.opacity[ids][None, :] * G
-            a = a_raw + (torch.clamp_max(a_raw, ALPHA_CAP) - a_raw).detach()
+            # min(0.99f, x) in CUDA is fminf: a NaN product (NaN opacity) yields 0.99, not NaN
+            a_cap = torch.fmin(a_raw.detach(), torch.tensor(ALPHA_CAP, dtype=dt))
+            a = torch.where(torch.isnan(a_raw.detach()), a_cap, a_raw + (a_cap - a_raw.detach()))
             valid = (power <= 0) & (a >= ALPHA_MIN)
             a_eff = torch.where(valid, a, torch.zeros((), dtype=dt))
             cp = torch.cumprod(torch.cat([Tcur[:, None], 1 - a_eff], 1), dim=1)

