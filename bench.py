@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--sh-degree", type=int, default=None)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: on, falling back to eager enqueue if capture fails)")
-    ap.add_argument("--variant", default="native", choices=["native", "standin", "packed_bwd", "rescan_bwd", "rescan_packed_bwd"],
+    ap.add_argument("--variant", default="native", choices=["native", "standin", "replay_bwd", "rescan_bwd", "rescan_packed_bwd"],
                     help="standin = reference-STRUCTURE kernels of csrc/standin.cu + 64-bit key sort + per-view "
                          "Python loop, for context only (never the reference, never the product)")
     ap.add_argument("--view-sharding", default="interleaved", choices=["balanced", "interleaved"],

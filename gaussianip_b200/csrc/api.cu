@@ -281,15 +281,15 @@ int gsb_render_bwd(const GsbSettings* s, int P, const void* saved, void* scratch
                               at<float>(saved, L.off_final_T), dL_dcolor, dL_ddepth, dL_dalpha,
                               at<GGrad>(scratch, L.off_ggrad), s->debug != 0, (cudaStream_t)stream);
   if (s->forward_only) return GSB_E_INVALID;       // that forward kept nothing for a backward pass
-  // variants: 0 replay + butterfly (default), 2 replay + packed reduction, 3 rescan + butterfly (the round-1
+  // variants: 0 transposed replay (default), 2 per-hit replay + butterfly, 3 rescan + butterfly (the round-1
   // kernel, record-free), 4 rescan + packed reduction
   const int variant = g_blend_variant.load();
   return launch_render_bwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order),
                            at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T),
                            at<uint2>(saved, L.off_hits), at<uint32_t>(saved, L.off_hit_count), dL_dcolor, dL_ddepth,
-                           dL_dalpha, at<GGrad>(scratch, L.off_ggrad), variant == 0 || variant == 2,
-                           variant == 2 || variant == 4, s->debug != 0, (cudaStream_t)stream);
+                           dL_dalpha, at<GGrad>(scratch, L.off_ggrad), variant == 0 ? 0 : (variant == 2 ? 1 : 2),
+                           variant == 4, s->debug != 0, (cudaStream_t)stream);
 }
 
 int gsb_preprocess_bwd_views(int V, const GsbSettings* const* settings, int P, int K, const float* means3D,

@@ -174,7 +174,7 @@ int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_lis
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
                       const float* final_T, const uint2* hits, const uint32_t* hit_count, const float* dL_dcolor,
-                      const float* dL_ddepth, const float* dL_dalpha, GGrad* ggrad, bool replay, bool packed,
+                      const float* dL_ddepth, const float* dL_dalpha, GGrad* ggrad, int kind, bool packed,
                       bool debug, cudaStream_t st);
 
 // reference-structure stand-in blend kernels (standin.cu; measurement context and cross-check only)

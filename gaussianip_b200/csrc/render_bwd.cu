@@ -551,13 +551,201 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
   cp_async_wait<0>();
 }
 
+
+// ---- transposed replay kernel (default) ---------------------------------------------------------------------------
+// The replay kernel above still evaluates one (half, Gaussian) hit per warp iteration, with ~9 of 32 lanes holding a
+// pixel the Gaussian really touched: 110 warp instructions per record (ncu r2d/r2e), most of them issued for idle
+// lanes, 56 of them the shuffle butterfly.  This kernel splits a block of 32 records into two phases that both run
+// with (nearly) every lane busy:
+//   phase 1, lane = PIXEL: each lane walks, back to front, only the records of the block whose mask names it (the
+//     32x32 bit matrix {record, lane} is transposed with five shuffles), runs the sequential part of the backward —
+//     weight, alpha, transmittance, suffix sum — and leaves the two numbers the rest needs, u = G dL/dalpha and
+//     w = alpha T, in a packed shared-memory slab (slot = prefix count of the record + rank of the lane in its mask);
+//   phase 2, lane = RECORD: each lane owns one record of the block, loops over that record's pixels reading (u, w)
+//     from the slab and the pixel's constants from two small tables, accumulates the ten sums in registers and
+//     sends them to the Gaussian's gradient record with three 16-byte reductions.
+// No butterfly, no per-hit atomics by idle lanes; a block costs max_lane(#records of a pixel) + max_record(#pixels)
+// short iterations instead of 32 (or max(|A|,|B|)) long ones.
+constexpr int T2_CAP = 512;            // (pixel, record) pairs per pass: 16 records x 32 lanes always fit
+constexpr size_t T2_WARP_BYTES = (size_t)STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint2)) +
+                                 T2_CAP * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2) + 32 * sizeof(uint32_t);
+
+// 32x32 bit-matrix transpose across the warp: bit r of the result in lane l = bit l of x in lane r
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const uint32_t mlo = sft == 16 ? 0x0000ffffu : sft == 8 ? 0x00ff00ffu : sft == 4 ? 0x0f0f0f0fu
+                         : sft == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, sft);
+    x = (lane & sft) ? ((x & ~mlo) | ((y >> sft) & mlo)) : ((x & mlo) | ((y << sft) & ~mlo));
+  }
+  return x;
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+render_bwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint2* __restrict__ ranges,
+                             const uint32_t* __restrict__ tile_order, const uint2* __restrict__ hits,
+                             const uint32_t* __restrict__ hit_count, const float* __restrict__ final_T,
+                             const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
+                             const float* __restrict__ dL_dalpha, GGrad* __restrict__ ggrad) {
+  extern __shared__ float4 smem_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  char* wbase = reinterpret_cast<char*>(smem_dyn) + (size_t)warp * T2_WARP_BYTES;
+  float4 (*ring)[3][32] = reinterpret_cast<float4 (*)[3][32]>(wbase);                          // [STAGES][3][32]
+  uint2 (*mring)[32] = reinterpret_cast<uint2 (*)[32]>(wbase + STAGES * 3 * 32 * sizeof(float4));   // [STAGES][32]
+  float2* slab = reinterpret_cast<float2*>(wbase + STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint2)));
+  float4* s_pg = reinterpret_cast<float4*>(slab + T2_CAP);        // per pixel: dL/dD, dL/dC0, dL/dC1, dL/dC2
+  float2* s_pxy = reinterpret_cast<float2*>(s_pg + 32);           // per pixel: x, y
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(s_pxy + 32);      // per record of the block: first slab slot
+
+  const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
+  const int tx = tile % v.gx, ty = tile / v.gx;
+  const int n_rec = (int)hit_count[tile * WARPS + warp];
+  if (n_rec == 0) return;
+  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  const int pix_x = tx * TILE_X + wx + lane_px(lane);
+  const int pix_y = ty * TILE_Y + wy + lane_py(lane);
+  const bool inside = pix_x < v.W && pix_y < v.H;
+  const float pxf = (float)pix_x, pyf = (float)pix_y;
+  const size_t hw = (size_t)v.H * v.W;
+  const size_t pix = (size_t)pix_y * v.W + pix_x;
+  const uint2 range = ranges[tile];
+  const uint2* recs = hits + ((size_t)range.x * WARPS + (size_t)warp * (size_t)(range.y - range.x));
+  const int blocks = (n_rec + 31) >> 5;
+
+  const float T_final = inside ? final_T[pix] : 0.0f;
+  float T = T_final;
+  const float gC0 = inside ? dL_dcolor[pix] : 0.f, gC1 = inside ? dL_dcolor[hw + pix] : 0.f,
+              gC2 = inside ? dL_dcolor[2 * hw + pix] : 0.f;
+  const float gD = inside ? dL_ddepth[pix] : 0.f, gA = inside ? dL_dalpha[pix] : 0.f;
+  const float bg_dot = v.bg[0] * gC0 + v.bg[1] * gC1 + v.bg[2] * gC2;
+  float Bdot = T_final * bg_dot;     // suffix sum, see render_bwd_kernel
+  s_pg[lane] = make_float4(gD, gC0, gC1, gC2);
+  s_pxy[lane] = make_float2(pxf, pyf);
+
+  // block index c counts from the BACK: it covers records [(blocks-1-c)*32, +32)
+  auto fetch_rec = [&](int c) -> uint2 {
+    if (c >= blocks) return make_uint2(0u, 0u);
+    const int e = (blocks - 1 - c) * 32 + lane;
+    return e < n_rec ? recs[e] : make_uint2(0u, 0u);
+  };
+  auto issue = [&](int c, uint2 rec) {
+    if (c < blocks) {
+      const int e = (blocks - 1 - c) * 32 + lane;
+      if (e < n_rec) {
+        const float4* src = reinterpret_cast<const float4*>(geom + rec.x);
+        float4 (*st)[32] = ring[c & (STAGES - 1)];
+        cp_async16(&st[0][lane], src);
+        cp_async16(&st[1][lane], src + 1);
+        cp_async16(&st[2][lane], src + 2);
+      }
+      mring[c & (STAGES - 1)][lane] = rec;        // (0, 0) beyond the end: no pixels
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int c = 0; c < STAGES - 1; ++c) issue(c, fetch_rec(c));
+  uint2 rec_next = fetch_rec(STAGES - 1);
+
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int c = 0; c < blocks; ++c) {
+    issue(c + STAGES - 1, rec_next);
+    rec_next = fetch_rec(c + STAGES);
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    float4 (*st)[32] = ring[c & (STAGES - 1)];
+    const uint2* meta = mring[c & (STAGES - 1)];
+    const uint2 my_rec = meta[lane];                       // this lane's record of the block (phase 2)
+    const int cnt = __popc(my_rec.y);
+    // exclusive prefix of the records' pixel counts = first slab slot of each record
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int my_off = incl - cnt;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    s_off[lane] = (uint32_t)my_off;
+    const uint32_t mine = transpose32(my_rec.y, lane);     // records of the block that name this lane's pixel
+    __syncwarp();
+    // one pass when the block's pairs fit the slab, else the back 16 records first, then the front 16
+    const int passes = total <= T2_CAP ? 1 : 2;
+    for (int ps = 0; ps < passes; ++ps) {
+      const int lo = passes == 1 ? 0 : (ps == 0 ? 16 : 0);
+      const int hi = passes == 1 ? 32 : (ps == 0 ? 32 : 16);
+      const uint32_t sel = passes == 1 ? 0xffffffffu : (ps == 0 ? 0xffff0000u : 0x0000ffffu);
+      const int base = (int)s_off[lo];
+      // ---- phase 1: lane = pixel -------------------------------------------------------------------------
+      uint32_t pend = mine & sel;
+      while (__any_sync(0xffffffffu, pend != 0u)) {
+        const int r = 31 - __clz(pend);                    // back to front; -1: this pixel has nothing left
+        if (r >= 0) {
+          pend &= ~(1u << r);
+          const uint32_t m = meta[r].y;
+          const int slot = (int)s_off[r] - base + __popc(m & lt);
+          const float4 a = st[0][r];
+          const float4 q = st[1][r];
+          const float4 f = st[2][r];
+          const float dx = a.x - pxf, dy = a.y - pyf;
+          const float G = exp2_blend(gauss_exponent2(q.x, q.y, q.z, dx, dy));
+          const float alpha = fminf(ALPHA_CAP, q.w * G);
+          const float inv1ma = rcp_blend(1.0f - alpha);
+          T *= inv1ma;
+          const float w = alpha * T;
+          const float phi = f.y * gC0 + f.z * gC1 + f.w * gC2 + f.x * gD + gA;
+          const float dL_da = T * phi - Bdot * inv1ma;
+          Bdot += phi * w;
+          slab[slot] = make_float2(G * dL_da, w);
+        }
+      }
+      __syncwarp();
+      // ---- phase 2: lane = record ------------------------------------------------------------------------
+      if (lane >= lo && lane < hi && cnt > 0) {
+        const float4 a = st[0][lane];
+        const float o = st[1][lane].w;
+        uint32_t m = my_rec.y;
+        const float2* src = slab + (my_off - base);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f, s8 = 0.f, s9 = 0.f;
+        while (m) {
+          const int p = __ffs(m) - 1;
+          m &= m - 1;
+          const float2 uw = *src++;
+          const float2 xy = s_pxy[p];
+          const float4 pg = s_pg[p];
+          const float dx = a.x - xy.x, dy = a.y - xy.y;
+          // raw moments of s = dL/dG * G about the splat centre (mapped to d(ndc xy), d(conic) in preprocess_bwd)
+          const float sv = o * uw.x;
+          const float sx = sv * dx, sy = sv * dy;
+          s0 += sx; s1 += sy; s2 += sx * dx; s3 += sx * dy; s4 += sy * dy;
+          s5 += uw.x;
+          s6 += uw.y * pg.x; s7 += uw.y * pg.y; s8 += uw.y * pg.z; s9 += uw.y * pg.w;
+        }
+        float* dst = reinterpret_cast<float*>(ggrad + my_rec.x);
+        red_add_v4(dst, s0, s1, s2, s3);
+        red_add_v4(dst + 4, s4, s5, s6, s7);
+        red_add_v4(dst + 8, s8, s9, 0.0f, 0.0f);
+      }
+      __syncwarp();                                        // the slab is rewritten by the next pass / block
+    }
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace
 
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,
                       const float* final_T, const uint2* hits, const uint32_t* hit_count, const float* dL_dcolor,
-                      const float* dL_ddepth, const float* dL_dalpha, GGrad* ggrad, bool replay, bool packed,
+                      const float* dL_ddepth, const float* dL_dalpha, GGrad* ggrad, int kind, bool packed,
                       bool debug, cudaStream_t st) {
+  // kind 0: transposed replay (default), 1: per-hit replay (butterfly), 2: rescan (record-free)
+  const bool replay = kind == 1;
   GSB_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)P * sizeof(GGrad), st));
   const int T = v.gx * v.gy;
   if (T == 0 || P == 0) return GSB_OK;
@@ -580,7 +768,16 @@ int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* po
                                   (int)(ring_replay + GSB_BWD_SMEM_PAD)));
     GSB_CUDA(cudaFuncSetAttribute(render_bwd_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(ring_replay + slab_bytes + GSB_BWD_SMEM_PAD)));
+    GSB_CUDA(cudaFuncSetAttribute(render_bwd_transposed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(WARPS * T2_WARP_BYTES + GSB_BWD_SMEM_PAD)));
     configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  if (kind == 0) {
+    if (!hits || !hit_count) return GSB_E_INVALID;
+    render_bwd_transposed_kernel<<<T, WARPS * 32, WARPS * T2_WARP_BYTES + GSB_BWD_SMEM_PAD, st>>>(
+        v, geom, ranges, tile_order, hits, hit_count, final_T, dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
+    GSB_POST_LAUNCH(debug, st, "render_bwd_transposed_kernel");
+    return GSB_OK;
   }
   if (replay) {
     if (!hits || !hit_count) return GSB_E_INVALID;

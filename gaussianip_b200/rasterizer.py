@@ -387,15 +387,15 @@ def stats() -> dict:
     return dict(_stats)
 
 
-BLEND_VARIANTS = {"native": 0, "standin": 1, "packed_bwd": 2, "rescan_bwd": 3, "rescan_packed_bwd": 4}
+BLEND_VARIANTS = {"native": 0, "standin": 1, "replay_bwd": 2, "rescan_bwd": 3, "rescan_packed_bwd": 4}
 
 
 def set_blend_variant(name: str) -> None:
     """'native' (default, the product kernels: the forward blend records per-warp hit lists, the backward replays
-    them), 'standin' (reference-STRUCTURE blend kernels of csrc/standin.cu, for measurement context and GPU
-    cross-checks only), 'packed_bwd' (replay backward with a packed shared-memory reduction instead of the per-hit
-    butterfly), 'rescan_bwd' (the record-free round-1 backward that re-walks the tile lists; cross-check of the replay
-    kernel) or 'rescan_packed_bwd'."""
+    them in two transposed phases, lane = pixel then lane = record), 'standin' (reference-STRUCTURE blend kernels of
+    csrc/standin.cu, for measurement context and GPU cross-checks only), 'replay_bwd' (replays the records one hit per
+    half-warp at a time with a shuffle butterfly), 'rescan_bwd' (the record-free round-1 backward that re-walks the
+    tile lists) or 'rescan_packed_bwd'; the last three are cross-checks of the default."""
     _lib.check(_lib.load().gsb_set_blend_variant(BLEND_VARIANTS[name]), "gsb_set_blend_variant")
 
 

@@ -278,14 +278,15 @@ int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, c
                     long long n_rows, const int64_t* index, long long dst_row0, void* stream);
 
 /* Blend-kernel variant used by gsb_render_fwd / gsb_render_bwd (process-wide, default 0):
- *   0  native kernels (the product path): forward blend records per-warp hit lists, backward blend replays them;
+ *   0  native kernels (the product path): the forward blend records per-warp hit lists, the backward blend replays
+ *      them in two transposed phases (lane = pixel: sequential part; lane = record: the ten sums);
  *   1  reference-STRUCTURE stand-in (csrc/standin.cu): thread per pixel, CTA-synchronous batches, no
  *      culling, per-pixel global atomics — for measurement context and as a GPU cross-check only;
- *   2  native forward + replay backward with a packed shared-memory reduction instead of the per-hit shuffle
- *      butterfly (csrc/render_bwd.cu, PACKED);
+ *   2  native forward + replay backward that takes one hit per half-warp at a time and reduces with a shuffle
+ *      butterfly (cross-check of 0);
  *   3  native forward + the record-free backward that re-walks the tile lists with per-warp culling (the
- *      round-1 kernel; cross-check of the replay kernel);
- *   4  as 3 with the packed reduction. */
+ *      round-1 kernel; cross-check of 0);
+ *   4  as 3 with a packed shared-memory reduction. */
 int gsb_set_blend_variant(int variant);
 
 /* Test / measurement helpers. */

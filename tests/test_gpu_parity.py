@@ -516,13 +516,13 @@ def test_fused_activations_equal_torch_getters(cuda_device, deg, multistream):
     _grad_close("viewspace", vb, va)
 
 
-@pytest.mark.parametrize("variant", ["packed_bwd", "rescan_bwd", "rescan_packed_bwd"])
+@pytest.mark.parametrize("variant", ["replay_bwd", "rescan_bwd"])
 @pytest.mark.parametrize("name", list(SCENES))
 def test_backward_variants_meet_the_same_bar(cuda_device, name, variant):
-    """The default backward blend REPLAYS the hit records the forward wrote; 'rescan_bwd' is the record-free
-    kernel that re-walks the tile lists with per-warp culling (round 1), 'packed_*' reduce through a packed
-    shared-memory slab instead of the shuffle butterfly.  All of them must meet the oracle bar, and — being the same
-    arithmetic over the same (pixel, Gaussian) pairs — agree with the default kernel to summation order."""
+    """The default backward blend REPLAYS the hit records the forward wrote, in two transposed phases; 'replay_bwd'
+    replays them one hit per half-warp at a time (shuffle butterfly), 'rescan_bwd' is the record-free kernel that
+    re-walks the tile lists with per-warp culling (round 1).  All of them must meet the oracle bar, and — being the
+    same arithmetic over the same (pixel, Gaussian) pairs — agree with the default kernel to summation order."""
     from gaussianip_b200 import rasterizer as R
     scene = util.humanoid_scene(**SCENES[name])
     w = util.loss_weights(scene.H, scene.W)
