@@ -407,6 +407,22 @@ class TrainWorkload:
         return cs
 
 
+def finish(world, rc=0):
+    """End of a run.  N > 1: every rank meets at a barrier, flushes and leaves with os._exit — tearing the process
+    group down while CUDA graphs that captured collective / symmetric-memory kernels are alive can hang."""
+    if world > 1:
+        import torch.distributed as dist
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(rc)
+    return rc
+
+
 def barrier(world):
     import torch.distributed as dist
     if world > 1:
@@ -736,10 +752,9 @@ def training_arm(a, rank, world, local_rank):
         except Exception as ex:                       # noqa: BLE001 -- the headline line must still be printed
             vcr = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
 
+    rc = 0 if (check is None or check.get("ok", True)) else 3
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0 if (check is None or check.get("ok", True)) else 3
+        return finish(world, rc)
 
     peaks = {}
     try:
@@ -795,9 +810,7 @@ def training_arm(a, rank, world, local_rank):
     if vcr is not None:
         line["vcr"] = vcr
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0 if (check is None or check.get("ok", True)) else 3
+    return finish(world, rc)
 
 
 # ---- our arm: playback (forward only) ---------------------------------------------------------------------------
@@ -995,9 +1008,7 @@ def playback_arm(a, rank, world, local_rank):
                         "d2h_bytes_per_step": res * res * 12},
                 "gpu_launches": int(launches), "roofline": None, "cpu_baseline": cpu}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return finish(world, 0)
 
 
 def main():

@@ -3,6 +3,7 @@ there is no CPU fallback and no other backend."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -67,6 +68,7 @@ _PROTOS = {
     "gsb_set_blend_variant": (C.c_int, [C.c_int]),
     "gsb_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "gsb_exchange_config": (C.c_int, [C.c_int, C.c_int, C.c_longlong, _P]),
+    "gsb_exchange_set_aux": (C.c_int, [_P, _P, _P]),
     "gsb_exchange_gather": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "gsb_mask_index_tmp_bytes": (C.c_size_t, [C.c_longlong]),
     "gsb_mask_to_index": (C.c_int, [C.c_longlong, _P, _P, _P, _P, _P]),
@@ -99,6 +101,10 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.gsb_abi_version() != ABI_VERSION:
         raise RuntimeError("libgsb.so ABI version mismatch; rebuild")
+    # A/B switch for measurements and for running the whole parity suite on the other forward blend kernel
+    fv = os.environ.get("GSB_FWD_VARIANT")
+    if fv:
+        lib.gsb_set_blend_variant({"per_hit": 10, "transposed": 11}[fv])
     _lib = lib
     return lib
 

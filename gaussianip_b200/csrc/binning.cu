@@ -12,6 +12,8 @@
 //                      keys (the reference's structure; kept for cross-checks).
 // Everything that depends on D reads it from device memory (counts[CNT_D]); grids are sized
 // by the capacity D_cap, so the host never synchronises to learn D.
+#include <atomic>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -496,15 +498,15 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
   uint32_t* status = counters + 256;
   constexpr size_t smem = onesweep_smem_bytes<KeyT>();
   {
-    static bool configured[64] = {};   // the attribute is per device and per instantiation
+    static std::atomic<unsigned long long> configured{0};   // bit per device (the attribute is per device and instantiation)
     int dev = 0;
     GSB_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
+    if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
       GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
       GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      configured[dev & 63] = true;
+      configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
   }
   if (!hist0_ready) {

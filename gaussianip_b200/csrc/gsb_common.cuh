@@ -168,8 +168,8 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
 
 int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
-                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool debug,
-                      cudaStream_t st);
+                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool transposed,
+                      bool debug, cudaStream_t st);
 
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, const uint32_t* n_contrib,

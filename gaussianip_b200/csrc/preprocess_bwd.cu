@@ -8,6 +8,9 @@
 // land in one gradient bucket.  The kernel takes up to GSB_MAX_VIEWS views at once: the
 // per-view contributions are summed in registers and every output is written ONCE, instead of
 // one read-modify-write of all gradient tensors per view.
+#include <atomic>
+#include <mutex>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -534,6 +537,7 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(const float* __res
 }  // namespace
 
 static ExchangePeers g_peers = {};
+static std::mutex g_peers_mu;       // autograd may run the backward on its own thread
 
 int set_exchange_peers(int world, int rank, long long rows_per_rank, const void* const* bases) {
   if (world < 1 || world > GSB_MAX_RANKS || rank < 0 || rank >= world || rows_per_rank <= 0 || (rows_per_rank & 31) || !bases)
@@ -544,6 +548,7 @@ int set_exchange_peers(int world, int rank, long long rows_per_rank, const void*
     if (!bases[r]) return GSB_E_INVALID;
     x.base[r] = static_cast<char*>(const_cast<void*>(bases[r]));
   }
+  std::lock_guard<std::mutex> lk(g_peers_mu);
   x.radii_max = g_peers.radii_max; x.scalar_in = g_peers.scalar_in; x.scalar_out = g_peers.scalar_out;
   g_peers = x;
   return GSB_OK;
@@ -551,6 +556,7 @@ int set_exchange_peers(int world, int rank, long long rows_per_rank, const void*
 
 int set_exchange_aux(int32_t* radii_max, const float* scalar_in, float* scalar_out) {
   if ((scalar_in != nullptr) != (scalar_out != nullptr)) return GSB_E_INVALID;
+  std::lock_guard<std::mutex> lk(g_peers_mu);
   g_peers.radii_max = radii_max; g_peers.scalar_in = scalar_in; g_peers.scalar_out = scalar_out;
   return GSB_OK;
 }
@@ -581,8 +587,13 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
                           cudaStream_t st) {
   if (P == 0) return GSB_OK;
   if (B.V < 1 || B.V > GSB_MAX_VIEWS) return GSB_E_INVALID;
-  if (accumulate == 3 && g_peers.world < 1) return GSB_E_INVALID;     // gsb_exchange_config was not called
-  if (accumulate == 2 && g_peers.world < 1) { g_peers.world = 1; g_peers.rank = 0; g_peers.rows_per_rank = 32; }
+  ExchangePeers peers;                       // snapshot of the process-wide table for this launch
+  {
+    std::lock_guard<std::mutex> lk(g_peers_mu);
+    peers = g_peers;
+  }
+  if (accumulate == 3 && peers.world < 1) return GSB_E_INVALID;       // gsb_exchange_config was not called
+  if (accumulate == 2 && peers.world < 1) { peers.world = 1; peers.rank = 0; peers.rows_per_rank = 32; }
   const int deg = B.a[0].v.sh_degree;
   for (int v = 1; v < B.V; ++v)
     if (B.a[v].v.sh_degree != deg) return GSB_E_INVALID;   // one degree per launch
@@ -593,30 +604,30 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
 #define GSB_LAUNCH_BWD(D)                                                                                       \
   do {                                                                                                          \
     if (smem > 48 * 1024) {                                                                                     \
-      static bool configured[64] = {};                                                                          \
+      static std::atomic<unsigned long long> configured{0};                                                     \
       int dev = 0;                                                                                              \
       GSB_CUDA(cudaGetDevice(&dev));                                                                            \
-      if (!configured[dev & 63]) {                                                                              \
+      if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {                                 \
         GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       64 * 1024));                                                              \
-        configured[dev & 63] = true;                                                                            \
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);                                     \
       }                                                                                                         \
     }                                                                                                           \
     if (accumulate == 2)                                                                                        \
       preprocess_bwd_kernel<D, 2><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
                                                            dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
                                                            colors ? dcolors : nullptr, dopac, dscales,          \
-                                                           drots, dcov3D, accumulate, g_peers);                 \
+                                                           drots, dcov3D, accumulate, peers);                 \
     else if (accumulate == 3)                                                                                   \
       preprocess_bwd_kernel<D, 3><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
                                                            dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
                                                            colors ? dcolors : nullptr, dopac, dscales,          \
-                                                           drots, dcov3D, accumulate, g_peers);                 \
+                                                           drots, dcov3D, accumulate, peers);                 \
     else                                                                                                        \
       preprocess_bwd_kernel<D, 0><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
                                                            dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
                                                            colors ? dcolors : nullptr, dopac, dscales,          \
-                                                           drots, dcov3D, accumulate, g_peers);                 \
+                                                           drots, dcov3D, accumulate, peers);                 \
   } while (0)
   switch (shs ? deg : 0) {
     case 0: GSB_LAUNCH_BWD(0); break;

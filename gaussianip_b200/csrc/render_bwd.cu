@@ -566,7 +566,11 @@ render_bwd_replay_kernel(View v, const Geom* __restrict__ geom, const uint2* __r
 //     sends them to the Gaussian's gradient record with three 16-byte reductions.
 // No butterfly, no per-hit atomics by idle lanes; a block costs max_lane(#records of a pixel) + max_record(#pixels)
 // short iterations instead of 32 (or max(|A|,|B|)) long ones.
-constexpr int T2_CAP = 512;            // (pixel, record) pairs per pass: 16 records x 32 lanes always fit
+#ifndef GSB_BWD_T2_CAP
+#define GSB_BWD_T2_CAP 512
+#endif
+constexpr int T2_CAP = GSB_BWD_T2_CAP;  // (pixel, record) pairs per pass; a record has at most 32
+static_assert(T2_CAP >= 32, "one record must fit");
 constexpr size_t T2_WARP_BYTES = (size_t)STAGES * (3 * 32 * sizeof(float4) + 32 * sizeof(uint2)) +
                                  T2_CAP * sizeof(float2) + 32 * sizeof(float4) + 32 * sizeof(float2) + 32 * sizeof(uint32_t);
 
@@ -587,7 +591,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-__global__ void __launch_bounds__(WARPS * 32)
+#ifndef GSB_BWD_T2_MINB
+#define GSB_BWD_T2_MINB 3
+#endif
+__global__ void __launch_bounds__(WARPS * 32, GSB_BWD_T2_MINB)
 render_bwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint2* __restrict__ ranges,
                              const uint32_t* __restrict__ tile_order, const uint2* __restrict__ hits,
                              const uint32_t* __restrict__ hit_count, const float* __restrict__ final_T,
@@ -674,13 +681,16 @@ render_bwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint2*
     s_off[lane] = (uint32_t)my_off;
     const uint32_t mine = transpose32(my_rec.y, lane);     // records of the block that name this lane's pixel
     __syncwarp();
-    // one pass when the block's pairs fit the slab, else the back 16 records first, then the front 16
-    const int passes = total <= T2_CAP ? 1 : 2;
-    for (int ps = 0; ps < passes; ++ps) {
-      const int lo = passes == 1 ? 0 : (ps == 0 ? 16 : 0);
-      const int hi = passes == 1 ? 32 : (ps == 0 ? 32 : 16);
-      const uint32_t sel = passes == 1 ? 0xffffffffu : (ps == 0 ? 0xffff0000u : 0x0000ffffu);
-      const int base = (int)s_off[lo];
+    // passes over runs of records whose pairs fit the slab, from the BACK of the block (one pass in most blocks)
+    (void)total;
+    int hi = 32;
+    while (hi > 0) {
+      // the longest run [lo, hi) with incl[hi-1] - off[lo] <= T2_CAP: lanes lo..hi-1 satisfy it (monotone in lo)
+      const int end = __shfl_sync(0xffffffffu, incl, hi - 1);
+      const uint32_t fm = __ballot_sync(0xffffffffu, lane < hi && end - my_off <= T2_CAP);
+      const int lo = hi - __popc(fm);
+      const uint32_t sel = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+      const int base = __shfl_sync(0xffffffffu, my_off, lo);
       // ---- phase 1: lane = pixel -------------------------------------------------------------------------
       uint32_t pend = mine & sel;
       while (__any_sync(0xffffffffu, pend != 0u)) {
@@ -712,6 +722,37 @@ render_bwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint2*
         uint32_t m = my_rec.y;
         const float2* src = slab + (my_off - base);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f, s8 = 0.f, s9 = 0.f;
+#ifndef GSB_BWD_T2_PIPE
+#define GSB_BWD_T2_PIPE 0
+#endif
+#if GSB_BWD_T2_PIPE
+        // software-pipelined: the next pixel's three shared-memory loads are in flight while this one is summed
+        int p = __ffs(m) - 1;
+        m &= m - 1;
+        float2 uw = *src++;
+        float2 xy = s_pxy[p];
+        float4 pg = s_pg[p];
+        while (true) {
+          const bool more = m != 0u;
+          float2 uwn = uw, xyn = xy;
+          float4 pgn = pg;
+          if (more) {
+            const int pn = __ffs(m) - 1;
+            m &= m - 1;
+            uwn = *src++;
+            xyn = s_pxy[pn];
+            pgn = s_pg[pn];
+          }
+          const float dx = a.x - xy.x, dy = a.y - xy.y;
+          const float sv = o * uw.x;
+          const float sx = sv * dx, sy = sv * dy;
+          s0 += sx; s1 += sy; s2 += sx * dx; s3 += sx * dy; s4 += sy * dy;
+          s5 += uw.x;
+          s6 += uw.y * pg.x; s7 += uw.y * pg.y; s8 += uw.y * pg.z; s9 += uw.y * pg.w;
+          if (!more) break;
+          uw = uwn; xy = xyn; pg = pgn;
+        }
+#else
         while (m) {
           const int p = __ffs(m) - 1;
           m &= m - 1;
@@ -726,12 +767,14 @@ render_bwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint2*
           s5 += uw.x;
           s6 += uw.y * pg.x; s7 += uw.y * pg.y; s8 += uw.y * pg.z; s9 += uw.y * pg.w;
         }
+#endif
         float* dst = reinterpret_cast<float*>(ggrad + my_rec.x);
         red_add_v4(dst, s0, s1, s2, s3);
         red_add_v4(dst + 4, s4, s5, s6, s7);
         red_add_v4(dst + 8, s8, s9, 0.0f, 0.0f);
       }
       __syncwarp();                                        // the slab is rewritten by the next pass / block
+      hi = lo;
     }
   }
   cp_async_wait<0>();

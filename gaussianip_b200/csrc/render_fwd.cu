@@ -237,12 +237,258 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
   }
 }
 
+
+// ---- transposed forward blend ------------------------------------------------------------------------------------
+// The kernel above evaluates one (half, Gaussian) hit per iteration with ~9 of 32 lanes on a pixel the splat reaches.
+// This one collects the hits of successive chunks into blocks of 32 and handles a block in two phases with
+// (nearly) every lane busy, like the transposed backward (render_bwd.cu):
+//   phase 1, lane = HIT: each lane owns one Gaussian of the block, walks the pixels of the warp's 8x4 block inside
+//     the Gaussian's conservative extent box (still-live pixels only) and writes their alphas — the same arithmetic,
+//     bit for bit, as the per-pixel evaluation — into a packed slab, remembering which reached 1/255;
+//   phase 2, lane = PIXEL: the 32x32 bit matrix {hit, pixel} is transposed with five shuffles and each lane blends,
+//     front to back, only the hits that reach ITS pixel (alpha from the slab, colour/depth row of the hit from
+//     shared memory): the transmittance chain, saturation test and contributor count are unchanged.
+// The masks of the pixels that really blended are transposed back into the per-warp hit records.
+constexpr int F2_CAP = 384;            // candidate (hit, pixel) pairs per pass; a hit has at most 32
+constexpr size_t F2_WARP_BYTES = (size_t)STAGES * 3 * 32 * sizeof(float4) + 3 * 32 * sizeof(float4) + 32 * sizeof(uint2) +
+                                 F2_CAP * sizeof(float) + 32 * sizeof(float2) + 2 * 32 * sizeof(uint32_t);
+
+__device__ __forceinline__ uint32_t transpose32_fwd(uint32_t x, int lane) {
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const uint32_t mlo = sft == 16 ? 0x0000ffffu : sft == 8 ? 0x00ff00ffu : sft == 4 ? 0x0f0f0f0fu
+                         : sft == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, sft);
+    x = (lane & sft) ? ((x & ~mlo) | ((y >> sft) & mlo)) : ((x & mlo) | ((y << sft) & ~mlo));
+  }
+  return x;
+}
+
+template <bool RECORD>
+__global__ void __launch_bounds__(WARPS * 32)
+render_fwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
+                             const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                             float* __restrict__ out_color, float* __restrict__ out_depth,
+                             float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
+                             float* __restrict__ final_T, uint2* __restrict__ hits, uint32_t* __restrict__ hit_count) {
+  extern __shared__ float4 smem_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  char* wbase = reinterpret_cast<char*>(smem_dyn) + (size_t)warp * F2_WARP_BYTES;
+  float4 (*ring)[3][32] = reinterpret_cast<float4 (*)[3][32]>(wbase);                       // [STAGES][3][32] candidates
+  float4 (*hb)[32] = reinterpret_cast<float4 (*)[32]>(wbase + STAGES * 3 * 32 * sizeof(float4));   // [3][32] hit block
+  uint2* hb_meta = reinterpret_cast<uint2*>(hb + 3);               // per hit: Gaussian id, list position + 1
+  float* slab = reinterpret_cast<float*>(hb_meta + 32);            // alphas of the candidate pairs of a pass
+  float2* s_pxy = reinterpret_cast<float2*>(slab + F2_CAP);        // per pixel (lane layout): x, y
+  uint32_t* s_bb = reinterpret_cast<uint32_t*>(s_pxy + 32);        // per hit: candidate pixels (extent box, live)
+  uint32_t* s_off = s_bb + 32;                                     // per hit: first slab slot
+
+  const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
+  const int tx = tile % v.gx, ty = tile / v.gx;
+  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  const int lx = lane_px(lane), ly = lane_py(lane);
+  const int pix_x = tx * TILE_X + wx + lx;
+  const int pix_y = ty * TILE_Y + wy + ly;
+  const bool inside = pix_x < v.W && pix_y < v.H;
+  const float pxf = (float)pix_x, pyf = (float)pix_y;
+  const float bx0 = (float)(tx * TILE_X + wx), by0 = (float)(ty * TILE_Y + wy);
+  s_pxy[lane] = make_float2(pxf, pyf);
+  // cull rectangle of the warp = bounding box of its pixels that are still accumulating
+  float cxw = bx0 + 3.5f, cyw = by0 + 1.5f, hwx = 3.5f, hwy = 1.5f;
+  uint32_t alive_prev = 0xffffffffu;
+
+  const uint2 range = ranges[tile];
+  const int n = (int)(range.y - range.x);
+  const int chunks = (n + 31) >> 5;
+  const uint32_t* pl = point_list + range.x;
+
+  float T = inside ? 1.0f : 0.0f, T_live = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f, A = 0.f;
+  uint32_t last = 0;
+  uint2* rec_base = RECORD ? hits + ((size_t)range.x * WARPS + (size_t)warp * (size_t)n) : nullptr;
+  int rec_n = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+
+  // one block of nb buffered hits (hb, hb_meta), in list order
+  auto process_block = [&](int nb) {
+    const uint32_t alive_now = __ballot_sync(0xffffffffu, T != 0.0f);
+    // ---- the candidate pixels of every hit: its extent box inside the 8x4 block, live pixels only ----
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), q = a;
+    uint32_t bb = 0u;
+    if (lane < nb) {
+      a = hb[0][lane];
+      q = hb[1][lane];
+      const int j0 = max(0, (int)ceilf(a.x - a.z - bx0)), j1 = min(7, (int)floorf(a.x + a.z - bx0));
+      const int i0 = max(0, (int)ceilf(a.y - a.w - by0)), i1 = min(3, (int)floorf(a.y + a.w - by0));
+      if (j1 >= j0 && i1 >= i0) {
+        const uint32_t xm = (2u << j1) - (1u << j0), ym = (2u << i1) - (1u << i0);
+        const uint32_t ysel = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);   // bits 0, 4, 8, 12
+        bb = (((xm & 15u) * ysel) | (((xm >> 4) * ysel) << 16)) & alive_now;
+      }
+    }
+    const int cntc = __popc(bb);
+    int incl = cntc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int off = incl - cntc;
+    s_bb[lane] = bb;
+    s_off[lane] = (uint32_t)off;
+    int lo = 0;
+    while (lo < nb) {
+      // as many hits as fit the slab (their candidate counts are a prefix sum, so the fitting lanes are a run)
+      const int base = __shfl_sync(0xffffffffu, off, lo);
+      const uint32_t fm = __ballot_sync(0xffffffffu, lane >= lo && lane < nb && incl - base <= F2_CAP);
+      const int hi = lo + __popc(fm);
+      // ---- phase 1: lane = hit ----
+      uint32_t vm = 0u;
+      if (lane >= lo && lane < hi) {
+        uint32_t m = bb;
+        float* dst = slab + (off - base);
+        while (m) {
+          const int p = __ffs(m) - 1;
+          m &= m - 1;
+          const float2 xy = s_pxy[p];
+          const float dx = a.x - xy.x, dy = a.y - xy.y;
+          const float e2 = gauss_exponent2(q.x, q.y, q.z, dx, dy);      // log2 of the Gaussian weight
+          const float al = e2 <= 0.0f ? fminf(ALPHA_CAP, q.w * exp2_blend(e2)) : 0.0f;
+          *dst++ = al;
+          if (al >= ALPHA_MIN) vm |= 1u << p;
+        }
+      }
+      __syncwarp();
+      // ---- phase 2: lane = pixel ----
+      uint32_t pend = transpose32_fwd(vm, lane);           // hits of this pass that reach this lane's pixel
+      uint32_t blended = 0u;
+      while (__any_sync(0xffffffffu, pend != 0u)) {
+        const int k = __ffs(pend) - 1;                      // front to back; -1: nothing left for this pixel
+        if (k >= 0) {
+          pend &= pend - 1;
+          const float al = slab[(int)s_off[k] - base + __popc(s_bb[k] & lt)];
+          const float test_T = T * (1.0f - al);
+          const bool ok = test_T >= T_MIN;
+          if (ok) {
+            const float4 ff = hb[2][k];                     // depth, r, g, b
+            const float w = al * T;
+            C0 += ff.y * w; C1 += ff.z * w; C2 += ff.w * w;
+            Dz += ff.x * w; A += w;
+            T_live = test_T;
+            last = hb_meta[k].y;
+            blended |= 1u << k;
+          }
+          T = ok ? test_T : 0.0f;       // a saturating splat (or a finished pixel) leaves T at 0
+        }
+      }
+      if (RECORD) {
+        const uint32_t rm = transpose32_fwd(blended, lane);   // lane = hit: the pixels that blended it
+        const uint32_t nz = __ballot_sync(0xffffffffu, rm != 0u);
+        if (rm) rec_base[rec_n + __popc(nz & lt)] = make_uint2(hb_meta[lane].x, rm);
+        rec_n += __popc(nz);
+      }
+      __syncwarp();                                         // the slab is rewritten by the next pass
+      lo = hi;
+    }
+  };
+
+  if (chunks > 0 && __any_sync(0xffffffffu, T != 0.0f)) {
+    auto issue = [&](int c, uint32_t gid) {      // stage chunk c (lane's instance) into the ring
+      if (c < chunks) {
+        if (c * 32 + lane < n) {
+          const float4* src = reinterpret_cast<const float4*>(geom + gid);
+          float4 (*st)[32] = ring[c & (STAGES - 1)];
+          cp_async16(&st[0][lane], src);
+          cp_async16(&st[1][lane], src + 1);
+          cp_async16(&st[2][lane], src + 2);
+        }
+      }
+      cp_async_commit();
+    };
+    auto fetch_gid = [&](int c) -> uint32_t {
+      const int e = c * 32 + lane;
+      return (c < chunks && e < n) ? pl[e] : 0u;
+    };
+    static_assert(STAGES == 2, "the ids of exactly one chunk are kept in flight");
+    uint32_t gid_cur = fetch_gid(0);
+    issue(0, gid_cur);
+    uint32_t gid_next = fetch_gid(1);
+    int nh = 0;                                   // hits buffered in hb
+    bool all_done = false;
+    for (int c = 0; c < chunks; ++c) {
+      const uint32_t gid_issued = gid_next;
+      issue(c + 1, gid_next);
+      gid_next = fetch_gid(c + 2);
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();
+      float4 (*st)[32] = ring[c & (STAGES - 1)];
+      const int e = c * 32 + lane;
+      const bool done = T == 0.0f;
+      const uint32_t alive = __ballot_sync(0xffffffffu, !done);
+      if (alive != alive_prev) {
+        alive_prev = alive;
+        const int x0 = __reduce_min_sync(0xffffffffu, done ? 64 : lx), x1 = __reduce_max_sync(0xffffffffu, done ? -1 : lx);
+        const int y0 = __reduce_min_sync(0xffffffffu, done ? 64 : ly), y1 = __reduce_max_sync(0xffffffffu, done ? -1 : ly);
+        hwx = 0.5f * (float)(x1 - x0); hwy = 0.5f * (float)(y1 - y0);
+        cxw = bx0 + (float)x0 + hwx; cyw = by0 + (float)y0 + hwy;
+      }
+      bool hit = false;
+      float4 r0, r1, r2;
+      if (e < n) {
+        r0 = st[0][lane];
+        hit = (fabsf(r0.x - cxw) <= r0.z + hwx) && (fabsf(r0.y - cyw) <= r0.w + hwy);
+      }
+      const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+      if (hm) {
+        const int cnt = __popc(hm);
+        const int pos = nh + __popc(hm & lt);
+        if (hit) { r1 = st[1][lane]; r2 = st[2][lane]; }
+        if (hit && pos < 32) {
+          hb[0][pos] = r0; hb[1][pos] = r1; hb[2][pos] = r2;
+          hb_meta[pos] = make_uint2(gid_cur, (uint32_t)(e + 1));
+        }
+        if (nh + cnt >= 32) {
+          __syncwarp();
+          process_block(32);
+          if (hit && pos >= 32) {
+            hb[0][pos - 32] = r0; hb[1][pos - 32] = r1; hb[2][pos - 32] = r2;
+            hb_meta[pos - 32] = make_uint2(gid_cur, (uint32_t)(e + 1));
+          }
+          nh = nh + cnt - 32;
+        } else {
+          nh += cnt;
+        }
+      }
+      gid_cur = gid_issued;
+      if (__all_sync(0xffffffffu, T == 0.0f)) { all_done = true; break; }
+      __syncwarp();                              // ring slot c is free before it is refilled
+    }
+    if (!all_done && nh > 0) {
+      __syncwarp();
+      process_block(nh);
+    }
+    cp_async_wait<0>();
+  }
+  if (RECORD && lane == 0) hit_count[tile * WARPS + warp] = (uint32_t)rec_n;
+
+  if (inside) {
+    T = T_live;
+    const size_t hw = (size_t)v.H * v.W;
+    const size_t pix = (size_t)pix_y * v.W + pix_x;
+    out_color[pix] = C0 + T * v.bg[0];
+    out_color[hw + pix] = C1 + T * v.bg[1];
+    out_color[2 * hw + pix] = C2 + T * v.bg[2];
+    out_depth[pix] = Dz;
+    out_alpha[pix] = A;
+    n_contrib[pix] = last;
+    final_T[pix] = T;
+  }
+}
+
 }  // namespace
 
 int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
-                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool debug,
-                      cudaStream_t st) {
+                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool transposed,
+                      bool debug, cudaStream_t st) {
   const int T = v.gx * v.gy;
   if (T == 0) return GSB_OK;
 #ifndef GSB_FWD_SMEM_PAD
@@ -255,7 +501,22 @@ int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_lis
   if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_transposed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(WARPS * F2_WARP_BYTES + GSB_FWD_SMEM_PAD)));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_transposed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(WARPS * F2_WARP_BYTES + GSB_FWD_SMEM_PAD)));
     configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  if (transposed) {
+    const size_t smem2 = WARPS * F2_WARP_BYTES + GSB_FWD_SMEM_PAD;
+    if (hits && hit_count)
+      render_fwd_transposed_kernel<true><<<T, WARPS * 32, smem2, st>>>(v, geom, point_list, ranges, tile_order, color,
+                                                                       depth, alpha, n_contrib, final_T, hits, hit_count);
+    else
+      render_fwd_transposed_kernel<false><<<T, WARPS * 32, smem2, st>>>(v, geom, point_list, ranges, tile_order, color,
+                                                                        depth, alpha, n_contrib, final_T, nullptr, nullptr);
+    GSB_POST_LAUNCH(debug, st, "render_fwd_transposed_kernel");
+    return GSB_OK;
   }
   if (hits && hit_count)
     render_fwd_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth,

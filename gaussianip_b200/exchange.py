@@ -34,7 +34,8 @@ import torch
 import torch.distributed as dist
 
 _FIELDS = (("means3D", 3), ("means2D", 3), ("opacities", 1), ("shs", None), ("colors", 3), ("scales", 3),
-           ("rotations", 4), ("cov3D", 6))
+           ("rotations", 4), ("cov3D", 6), ("radii", 1), ("scalars", None))
+SCALAR_SLOTS = 64        # the "scalars" field: a few floats summed over ranks (slot 0: the step's loss)
 
 
 def plan_layout(P: int, K: int, present: Dict[str, bool]):
@@ -44,7 +45,7 @@ def plan_layout(P: int, K: int, present: Dict[str, bool]):
     for name, w in _FIELDS:
         if not present.get(name, False):
             continue
-        shape = (P, K, 3) if name == "shs" else (P, w)
+        shape = (P, K, 3) if name == "shs" else ((SCALAR_SLOTS,) if name == "scalars" else (P, w))
         n = 1
         for d in shape:
             n *= d
@@ -62,6 +63,10 @@ def plan_ownership(P: int, layout, rank: int, world: int):
     r1 = P if rank == world - 1 else min(r0 + rows_per_rank, P)
     segments = []
     for name, (foff, shape) in layout.items():
+        if name == "scalars":                 # owned by rank 0 as a whole
+            if rank == 0:
+                segments.append((foff, shape[0]))
+            continue
         w = 1
         for d in shape[1:]:
             w *= d
@@ -180,6 +185,16 @@ class GradExchange:
         self.buf.zero_()
         self.hdl.barrier(channel=0)
         self.steps = 0
+
+    def set_aux(self, loss: Optional[torch.Tensor], first_launch: bool = True) -> None:
+        """Arm the extras of the next fused launch: the radii maximum always (when the buffer has the field), the
+        scalar `loss` only on the first launch of a backward (it must be added once)."""
+        import ctypes as C
+        from . import _lib
+        radii = self.output_ptr("radii")
+        sc = self.output_ptr("scalars") if (loss is not None and first_launch) else None
+        _lib.check(_lib.load().gsb_exchange_set_aux(radii, loss.data_ptr() if sc is not None else None, sc),
+                   "gsb_exchange_set_aux")
 
     def output_ptr(self, name: str) -> Optional[int]:
         """What the kernel is given for this field: the multicast address (push_all) or the local copy (owner_push)."""

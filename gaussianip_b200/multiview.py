@@ -221,6 +221,9 @@ class ViewParallel:
             else:
                 out = render_views_fn(local, b.viewspace_points)
             loss = loss_fn(local, out)
+            if self.exchange is not None:
+                # the step's loss is summed over ranks by the fused kernel too (no NCCL call in the step)
+                self.exchange.pending_scalar = loss.detach().to(torch.float32).reshape(1)
             loss.backward()
             return out["radii"], loss.detach().to(torch.float32)
 
@@ -231,12 +234,15 @@ class ViewParallel:
             if not local:
                 raise ValueError("fused exchange needs at least one view per rank")
             radii, total = body()
+            # radii maximum and loss sum came out of the fused kernel (exchange.set_aux): no NCCL in the step
+            radii = self.exchange.local("radii").view(torch.int32).reshape(-1).clone()
+            total = self.exchange.local("scalars")[0].clone()
         else:
             radii, total = self._attempt(body)
             b.all_reduce(self.group)
-        all_reduce_radii_max(radii, self.group)
-        if self.world > 1:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+            all_reduce_radii_max(radii, self.group)
+            if self.world > 1:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
         if direct:
             vg = b.viewspace_points.grad
             vg = vg if vg is not None else torch.zeros_like(b.viewspace_points)

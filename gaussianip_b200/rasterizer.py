@@ -78,16 +78,30 @@ class _Workspace:
         return self.scratch
 
 
-_workspaces = {}
+_workspaces = {}                # (device index, stream handle) -> _Workspace, most recently used last
+MAX_WORKSPACES = 64             # streams come and go; a dead stream's scratch block must not live forever
 
 
 def _workspace(device: torch.device) -> _Workspace:
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
+    ws = _workspaces.pop(key, None)
     if ws is None:
-        ws = _workspaces[key] = _Workspace(device)
+        ws = _Workspace(device)
+        while len(_workspaces) >= MAX_WORKSPACES:           # drop the least recently used (dicts keep insertion order)
+            old = _workspaces.pop(next(iter(_workspaces)))
+            if old.pending is not None:
+                old.pending.settle()
+    _workspaces[key] = ws
     return ws
+
+
+def release_workspaces() -> None:
+    """Free every per-stream scratch block (they are re-created on demand)."""
+    for ws in list(_workspaces.values()):
+        if ws.pending is not None:
+            ws.pending.settle()
+    _workspaces.clear()
 
 
 def set_binning_mode(mode: str, device=None) -> None:
@@ -387,7 +401,8 @@ def stats() -> dict:
     return dict(_stats)
 
 
-BLEND_VARIANTS = {"native": 0, "standin": 1, "replay_bwd": 2, "rescan_bwd": 3, "rescan_packed_bwd": 4}
+BLEND_VARIANTS = {"native": 0, "standin": 1, "replay_bwd": 2, "rescan_bwd": 3, "rescan_packed_bwd": 4,
+                  "fwd_per_hit": 10, "fwd_transposed": 11}
 
 
 def set_blend_variant(name: str) -> None:
@@ -473,10 +488,11 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
             # addresses; `out` are this rank's views of the symmetric buffer, `optr` what the kernel is given
             exchange.ensure(P, K, {"means3D": True, "means2D": True, "opacities": True, "shs": shs is not None,
                                    "colors": colors is not None, "scales": scales is not None,
-                                   "rotations": rotations is not None, "cov3D": cov3D is not None}, device)
+                                   "rotations": rotations is not None, "cov3D": cov3D is not None,
+                                   "radii": True, "scalars": True}, device)
             exchange.begin()                 # zero + barrier, overlaps the blend backward on the side streams
             out = {k: exchange.local(k) for k in ("means3D", "means2D", "opacities", "shs", "colors", "scales",
-                                                  "rotations", "cov3D")}
+                                                  "rotations", "cov3D")}     # ("radii" / "scalars": exchange.local)
             optr = {k: exchange.output_ptr(k) for k in out}
         else:
             out = {"means3D": e(P, 3), "means2D": e(P, 3), "opacities": e(P, 1),
@@ -527,6 +543,9 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
             svp = (C.c_void_p * n)(*[svs[v0 + j].block.data_ptr() for j in range(n)])
             scp = (C.c_void_p * n)(*[staged[j][2].data_ptr() for j in range(n)])
             dcp = (C.c_longlong * n)(*[svs[v0 + j].d_cap for j in range(n)])
+            if exchange is not None:
+                # the radii maximum (and, once per backward, the step's scalar) ride in the fused launch
+                exchange.set_aux(getattr(exchange, "pending_scalar", None), first_launch=v0 == 0)
             rc = lib.gsb_preprocess_bwd_views(n, sp, P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
                                               _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), rp, svp, scp,
                                               dcp, optr["means3D"], optr["means2D"], optr["shs"],

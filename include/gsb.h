@@ -259,6 +259,14 @@ int gsb_knn_dist2(long long P, const float* points, float* mean_dist2, void* scr
 #define GSB_MAX_RANKS 16
 #define GSB_EXCHANGE_MAX_SEGMENTS 8
 int gsb_exchange_config(int world, int rank, long long rows_per_rank, const void* const* peer_bases);
+/* Extras that ride in the next mode-2 / mode-3 launches of gsb_preprocess_bwd_views (process-wide, until changed):
+ *   radii_max   [P] int32 inside the symmetric buffer (multicast address in mode 2, local copy in mode 3; zero before
+ *               the step): receives the MAX over ranks of each Gaussian's largest radius over the launch's views;
+ *   scalar_in   one float on this device (e.g. the step's loss), added into scalar_out of every copy: scalar_out is
+ *               one float inside the symmetric buffer (multicast address in mode 2; in mode 3 the local address of
+ *               a slot owned by rank 0, which gsb_exchange_gather then distributes).
+ * NULL disables an extra.  With both, a view-sharded step needs no NCCL call at all. */
+int gsb_exchange_set_aux(int32_t* radii_max, const float* scalar_in, float* scalar_out);
 /* For each segment s < n_segments: floats [offset[s], offset[s] + count[s]) of the local copy are stored to the
  * same offsets of every copy through multicast_base (offsets multiples of 4 floats). */
 int gsb_exchange_gather(const float* local_base, float* multicast_base, int n_segments,
