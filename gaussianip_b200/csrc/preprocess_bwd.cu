@@ -316,7 +316,11 @@ view_contrib(const View& v, int i, const float* sV, const float* sM, const float
 #ifndef GSB_PBWD_MINB
 #define GSB_PBWD_MINB 2
 #endif
-template <int DEG, int MODE>     // MODE 0: store / accumulate locally, 2: multicast red into all copies, 3: red into the owner's copy
+// LPG = lanes per Gaussian (MODE 0 only): the views of a launch are dealt to LPG adjacent lanes, each lane loads and
+// differentiates its views, and the partial sums are added across the lanes with xor-shuffles.  The kernel is bound by
+// the latency of its per-view dependent loads at ~25 % occupancy (128 registers), so 4x more threads with a quarter
+// of the views each put 4x more loads in flight for the same arithmetic.
+template <int DEG, int MODE, int LPG>   // MODE 0: store / accumulate locally, 2: multicast red into all copies, 3: red into the owner's copy
 __global__ void __launch_bounds__(256, (DEG <= 1 ? GSB_PBWD_MINB : 2))
 preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rots,
@@ -335,7 +339,9 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
   for (int t = threadIdx.x; t < B.V * 3; t += blockDim.x) sCam[t / 3][t % 3] = B.a[t / 3].v.campos[t % 3];
   if (threadIdx.x >= 128 && threadIdx.x < 128 + B.V) load_intrinsics(B.a[threadIdx.x - 128].v, sK[threadIdx.x - 128]);
   __syncthreads();
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  static_assert(MODE == 0 || LPG == 1, "the exchange epilogue stages one row per lane");
+  const int i = (blockIdx.x * 256 + threadIdx.x) / LPG;
+  const int sub = threadIdx.x % LPG;
   // a Gaussian's coefficient row is K*12 contiguous bytes; the rows of a warp are contiguous too, so
   // reading one's own row touches every fetched sector completely (re-reads across views hit L1)
   const float* my_sh = shs ? shs + (size_t)i * K * 3 : nullptr;
@@ -352,6 +358,7 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
 #pragma unroll
   for (int k = 0; k < NC3; ++k) A.dsh[k] = 0.f;
 
+  const unsigned wm = __ballot_sync(0xffffffffu, i < P);     // the lanes that take the branch below (whole LPG groups)
   if (i < P) {
     // scale / rotation are loaded (and, for raw model parameters, activated) once for all views
     const int raw = B.a[0].v.raw;
@@ -372,6 +379,7 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
       if (rv > 0) seen |= 1u << vi;                                 // gradients of culled Gaussians are exactly 0
       rmax = max(rmax, rv);
     }
+    if (LPG > 1) seen &= (LPG == 4 ? 0x11u : 0x55u) << sub;          // this lane's share of the views
     const bool want_cl = dcolors == nullptr;
     ViewRec cur, nxt;
     int vi = seen ? __ffs(seen) - 1 : -1;
@@ -385,6 +393,30 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
       o_act = cur.con.w;                                            // activated opacity, as the forward stored it
       cur = nxt;
       vi = vn;
+    }
+    if (LPG > 1) {
+      // add the lanes' partial sums (all LPG lanes of a Gaussian are in one warp and take the same branches here)
+#pragma unroll
+      for (int d = 1; d < LPG; d <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          A.dp[k] += __shfl_xor_sync(wm, A.dp[k], d);
+          A.dsc[k] += __shfl_xor_sync(wm, A.dsc[k], d);
+          A.dcol[k] += __shfl_xor_sync(wm, A.dcol[k], d);
+        }
+        A.d2[0] += __shfl_xor_sync(wm, A.d2[0], d);
+        A.d2[1] += __shfl_xor_sync(wm, A.d2[1], d);
+        A.dop += __shfl_xor_sync(wm, A.dop, d);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) A.dq[k] += __shfl_xor_sync(wm, A.dq[k], d);
+        if (cov3Dp) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) A.dcov[k] += __shfl_xor_sync(wm, A.dcov[k], d);
+        }
+#pragma unroll
+        for (int k = 0; k < NC3; ++k) A.dsh[k] += __shfl_xor_sync(wm, A.dsh[k], d);
+        o_act = fmaxf(o_act, __shfl_xor_sync(wm, o_act, d));
+      }
     }
     // chain rule to the RAW parameters, applied once to the sum over views
     if (raw & GSB_RAW_OPACITY) A.dop = A.dop * (1.0f - o_act) * o_act;                    // sigmoid'
@@ -469,7 +501,7 @@ preprocess_bwd_kernel(BwdBatch B, int P, int K, const float* __restrict__ means3
     return;
   }
 
-  if (i < P) {
+  if (i < P && sub == 0) {
     put(dmeans3D + 3 * i, A.dp[0], acc); put(dmeans3D + 3 * i + 1, A.dp[1], acc); put(dmeans3D + 3 * i + 2, A.dp[2], acc);
     put(dmeans2D + 3 * i, A.d2[0], acc); put(dmeans2D + 3 * i + 1, A.d2[1], acc);
     if (!acc) dmeans2D[3 * i + 2] = 0.f;
@@ -601,6 +633,13 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
   const size_t smem = 0;
   (void)nc3;
   const int grid = (P + 255) / 256;
+  // lanes per Gaussian (local modes): 4 for three or more views, 2 for two, 1 otherwise; degree >= 2 keeps 1 (its
+  // 27-48 SH gradient sums per lane would cost more shuffles than the split saves)
+#ifndef GSB_PBWD_LPG
+#define GSB_PBWD_LPG 1
+#endif
+  const int lpg = (accumulate >= 2 || deg >= 2) ? 1
+                  : (B.V >= 3 ? (GSB_PBWD_LPG >= 4 ? 4 : GSB_PBWD_LPG) : (B.V == 2 && GSB_PBWD_LPG >= 2 ? 2 : 1));
 #define GSB_LAUNCH_BWD(D)                                                                                       \
   do {                                                                                                          \
     if (smem > 48 * 1024) {                                                                                     \
@@ -608,23 +647,31 @@ int launch_preprocess_bwd(const BwdBatch& B, int P, int K, const float* means3D,
       int dev = 0;                                                                                              \
       GSB_CUDA(cudaGetDevice(&dev));                                                                            \
       if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {                                 \
-        GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<D, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       64 * 1024));                                                              \
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);                                     \
       }                                                                                                         \
     }                                                                                                           \
     if (accumulate == 2)                                                                                        \
-      preprocess_bwd_kernel<D, 2><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
+      preprocess_bwd_kernel<D, 2, 1><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,       \
                                                            dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
                                                            colors ? dcolors : nullptr, dopac, dscales,          \
                                                            drots, dcov3D, accumulate, peers);                 \
     else if (accumulate == 3)                                                                                   \
-      preprocess_bwd_kernel<D, 3><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
+      preprocess_bwd_kernel<D, 3, 1><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,       \
                                                            dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
                                                            colors ? dcolors : nullptr, dopac, dscales,          \
                                                            drots, dcov3D, accumulate, peers);                 \
+    else if (lpg == 4)                                                                                          \
+      preprocess_bwd_kernel<D, 0, 4><<<(int)(((long long)P * 4 + 255) / 256), 256, smem, st>>>(                 \
+          B, P, K, means3D, scales, rots, shs, cov3D, dmeans3D, dmeans2D, shs ? dshs : nullptr,                 \
+          colors ? dcolors : nullptr, dopac, dscales, drots, dcov3D, accumulate, peers);                        \
+    else if (lpg == 2)                                                                                          \
+      preprocess_bwd_kernel<D, 0, 2><<<(int)(((long long)P * 2 + 255) / 256), 256, smem, st>>>(                 \
+          B, P, K, means3D, scales, rots, shs, cov3D, dmeans3D, dmeans2D, shs ? dshs : nullptr,                 \
+          colors ? dcolors : nullptr, dopac, dscales, drots, dcov3D, accumulate, peers);                        \
     else                                                                                                        \
-      preprocess_bwd_kernel<D, 0><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,          \
+      preprocess_bwd_kernel<D, 0, 1><<<grid, 256, smem, st>>>(B, P, K, means3D, scales, rots, shs, cov3D,       \
                                                            dmeans3D, dmeans2D, shs ? dshs : nullptr,            \
                                                            colors ? dcolors : nullptr, dopac, dscales,          \
                                                            drots, dcov3D, accumulate, peers);                 \

@@ -414,6 +414,17 @@ def set_blend_variant(name: str) -> None:
     _lib.check(_lib.load().gsb_set_blend_variant(BLEND_VARIANTS[name]), "gsb_set_blend_variant")
 
 
+_pbwd_group = int(__import__("os").environ.get("GSB_PBWD_GROUP", "8"))
+
+
+def set_backward_grouping(views_per_launch: int) -> None:
+    """How many views one launch of the fused per-Gaussian backward covers in rasterize_views (single GPU): 8 = one
+    launch per step (every gradient written once), smaller = more launches that overlap the blend backwards of the
+    remaining views (the later ones accumulate)."""
+    global _pbwd_group
+    _pbwd_group = max(1, int(views_per_launch))
+
+
 def set_multistream(enabled: bool) -> None:
     """Run the views of rasterize_views on separate CUDA streams (default) or back to back."""
     global _multistream
@@ -509,12 +520,14 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
 
         g_color, g_depth, g_alpha = grad_in(g_color, (V, 3, H, W)), grad_in(g_depth, (V, 1, H, W)), \
             grad_in(g_alpha, (V, 1, H, W))
-        streams = _streams_for(device, V)
+        # set_multistream(False) (measurement passes): everything on the calling stream, one view at a time — the views
+        # then share one scratch block, so each view's per-Gaussian launch follows its blend backward directly
+        streams = _streams_for(device, V) if _multistream else [main] * V
         # Groups of <= MAX_VIEWS views: their blend backwards run on the side streams (they overlap), then ONE fused
         # per-Gaussian kernel sums the group's contributions in registers and writes (first group) or accumulates
         # (later groups) every gradient tensor.  A side stream's scratch block holds the GGrad records of one view
         # at a time, so the next group's blend backward waits for this group's per-Gaussian kernel.
-        G = min(_lib.MAX_VIEWS, MAX_SIDE_STREAMS)
+        G = min(_lib.MAX_VIEWS, MAX_SIDE_STREAMS) if _multistream else 1
         for v0 in range(0, V, G):
             n = min(G, V - v0)
             fork = torch.cuda.Event()
@@ -523,7 +536,8 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
             for j in range(n):
                 v = v0 + j
                 rs, sv, st = settings_list[v], svs[v], streams[v]
-                st.wait_event(fork)
+                if st is not main:
+                    st.wait_event(fork)
                 with torch.cuda.stream(st):
                     ws = _workspace(device)
                     s, keep = _make_settings(rs, device, raw, None if tanfov_dev is None else tanfov_dev[v])
@@ -535,25 +549,32 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
                     done = torch.cuda.Event()
                     done.record(st)
                 staged.append((s, keep, scratch, done))
-            for j in range(n):
-                main.wait_event(staged[j][3])
-                svs[v0 + j].block.record_stream(main)
-            sp = (C.POINTER(_lib.GsbSettings) * n)(*[C.pointer(staged[j][0]) for j in range(n)])
-            rp = (C.c_void_p * n)(*[radii[v0 + j].data_ptr() for j in range(n)])
-            svp = (C.c_void_p * n)(*[svs[v0 + j].block.data_ptr() for j in range(n)])
-            scp = (C.c_void_p * n)(*[staged[j][2].data_ptr() for j in range(n)])
-            dcp = (C.c_longlong * n)(*[svs[v0 + j].d_cap for j in range(n)])
-            if exchange is not None:
-                # the radii maximum (and, once per backward, the step's scalar) ride in the fused launch
-                exchange.set_aux(getattr(exchange, "pending_scalar", None), first_launch=v0 == 0)
-            rc = lib.gsb_preprocess_bwd_views(n, sp, P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
-                                              _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), rp, svp, scp,
-                                              dcp, optr["means3D"], optr["means2D"], optr["shs"],
-                                              optr["colors"], optr["opacities"], optr["scales"],
-                                              optr["rotations"], optr["cov3D"],
-                                              exchange.mode if exchange is not None else int(v0 > 0),
-                                              main.cuda_stream)
-            _lib.check(rc, "gsb_preprocess_bwd_views")
+            # Per-Gaussian stage in sub-groups of `sub` views: a sub-group's launch waits only for ITS blend backwards,
+            # so it runs (memory-bound) underneath the blend backwards (issue-bound) of the views that follow; the
+            # first launch writes the gradient tensors, later ones accumulate.  With the fused exchange every launch
+            # adds into remote memory, so the whole group stays one launch there.
+            sub = n if exchange is not None else max(1, min(n, _pbwd_group))
+            for j0 in range(0, n, sub):
+                m = min(sub, n - j0)
+                for j in range(j0, j0 + m):
+                    main.wait_event(staged[j][3])
+                    svs[v0 + j].block.record_stream(main)
+                sp = (C.POINTER(_lib.GsbSettings) * m)(*[C.pointer(staged[j][0]) for j in range(j0, j0 + m)])
+                rp = (C.c_void_p * m)(*[radii[v0 + j].data_ptr() for j in range(j0, j0 + m)])
+                svp = (C.c_void_p * m)(*[svs[v0 + j].block.data_ptr() for j in range(j0, j0 + m)])
+                scp = (C.c_void_p * m)(*[staged[j][2].data_ptr() for j in range(j0, j0 + m)])
+                dcp = (C.c_longlong * m)(*[svs[v0 + j].d_cap for j in range(j0, j0 + m)])
+                if exchange is not None:
+                    # the radii maximum (and, once per backward, the step's scalar) ride in the fused launch
+                    exchange.set_aux(getattr(exchange, "pending_scalar", None), first_launch=v0 == 0)
+                rc = lib.gsb_preprocess_bwd_views(m, sp, P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
+                                                  _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), rp, svp, scp,
+                                                  dcp, optr["means3D"], optr["means2D"], optr["shs"],
+                                                  optr["colors"], optr["opacities"], optr["scales"],
+                                                  optr["rotations"], optr["cov3D"],
+                                                  exchange.mode if exchange is not None else int(v0 + j0 > 0),
+                                                  main.cuda_stream)
+                _lib.check(rc, "gsb_preprocess_bwd_views")
         if exchange is not None:
             exchange.end()                   # every rank's reds have landed: the local copy is the global sum
             if exchange.clone_outputs:
@@ -563,7 +584,8 @@ def _backward_views(settings_list, svs, means3D, shs, colors, opacities, scales,
         back = torch.cuda.Event()
         back.record(main)
         for st in set(streams):
-            st.wait_event(back)              # next use of a side workspace is ordered after these reads
+            if st is not main:
+                st.wait_event(back)          # next use of a side workspace is ordered after these reads
     return out
 
 
