@@ -94,7 +94,10 @@ constexpr uint32_t ST_AGG = 1u << 30, ST_PREFIX = 2u << 30, ST_MASK = (1u << 30)
 constexpr int MAX_PASSES = 8;
 // All blocks of a 1-2 M key pass are co-resident (one wave), so the inclusive prefix travels
 // down the chain of blocks one look-back round trip at a time: read LB predecessors per trip.
-constexpr int LB = 4;
+#ifndef GSB_RADIX_LB
+#define GSB_RADIX_LB 4
+#endif
+constexpr int LB = GSB_RADIX_LB;
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)

@@ -221,3 +221,35 @@ def test_batched_step_direct_gradients_and_two_ranks_agree_with_the_per_view_loo
         torch.testing.assert_close(ret[r]["vg"], res1["viewspace_grad"], rtol=1e-4, atol=1e-4)
         assert torch.equal(ret[r]["radii"], res1["radii"])
         torch.testing.assert_close(ret[r]["loss"], res1["loss"], rtol=1e-5, atol=1e-5)
+
+
+def test_exchange_plan_with_radii_scalars_and_tiny_clouds():
+    """The extras that ride in the fused exchange: the per-Gaussian radii (one int per row, owned like every other
+    row block) and the scalar slots (owned by rank 0 as a whole).  With P <= 32 (world - 1) some ranks own no rows at
+    all: their segment list is empty — they must still take part in every barrier (GradExchange.end launches
+    nothing for them but always meets the closing barrier)."""
+    from gaussianip_b200.exchange import SCALAR_SLOTS, plan_layout, plan_ownership
+    present = {"means3D": True, "means2D": True, "opacities": True, "shs": True, "scales": True, "rotations": True,
+               "radii": True, "scalars": True}
+    for P, world in ((5, 4), (40, 8), (1000, 2)):
+        layout, total = plan_layout(P, 1, present)
+        assert layout["radii"][1] == (P, 1) and layout["scalars"][1] == (SCALAR_SLOTS,)
+        owners_of_scalars, empty_ranks = [], 0
+        rows_seen = 0
+        for rank in range(world):
+            rpr, segs = plan_ownership(P, layout, rank, world)
+            names = []
+            for off, cnt in segs:
+                name = max((n for n in layout if layout[n][0] <= off), key=lambda n: layout[n][0])
+                names.append(name)
+                assert off + cnt <= total
+                if name == "radii":
+                    rows_seen += cnt
+            if "scalars" in names:
+                owners_of_scalars.append(rank)
+            if not [n for n in names if n != "scalars"]:
+                empty_ranks += 1
+        assert owners_of_scalars == [0]
+        assert rows_seen == P                                   # every Gaussian's radius has exactly one owner
+        if P <= 32 * (world - 1):
+            assert empty_ranks >= 1
