@@ -22,8 +22,11 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 8;
-constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 2048 keys per block
+#ifndef GSB_RADIX_IPT
+#define GSB_RADIX_IPT 8
+#endif
+constexpr int RS_IPT = GSB_RADIX_IPT;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;  // keys per block (2048 at 8 per thread)
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;

@@ -47,8 +47,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+#ifndef GSB_FWD_MINB
+#define GSB_FWD_MINB 1
+#endif
 template <bool RECORD>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, GSB_FWD_MINB)
 render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                   float* __restrict__ out_color,
