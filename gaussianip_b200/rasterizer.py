@@ -207,6 +207,8 @@ class _ForwardCall:
         self.out = out
         self.stream = None
         self.counts = None
+        self.mark_binned = False      # record self.binned between binning and blend (staggered multi-view forward)
+        self.binned = None
 
     def enqueue(self):
         lib = _lib.load()
@@ -242,6 +244,24 @@ class _ForwardCall:
             self.scratch = ws.ensure_scratch(self.L.scratch_bytes)
             self.block = torch.empty(self.L.saved_bytes_forward_only if self.forward_only else self.L.saved_bytes,
                                      dtype=torch.uint8, device=device)
+            if self.mark_binned:
+                # the three stages one by one, with an event between binning and blend: the NEXT view's pipeline
+                # is started behind it (rasterize_views, staggered forward)
+                st = self.stream.cuda_stream
+                rc = lib.gsb_preprocess_fwd(C.byref(self.s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
+                                            _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D),
+                                            self.radii.data_ptr(), self.block.data_ptr(), self.scratch.data_ptr(),
+                                            self.d_cap, st)
+                _lib.check(rc, "gsb_preprocess_fwd")
+                rc = lib.gsb_bin_sort(C.byref(self.s), P, self.block.data_ptr(), self.scratch.data_ptr(), self.d_cap,
+                                      ws.binning_mode, counts_ptr, event, st)
+                _lib.check(rc, "gsb_bin_sort")
+                self.binned = torch.cuda.Event()
+                self.binned.record(self.stream)
+                rc = lib.gsb_render_fwd(C.byref(self.s), P, self.block.data_ptr(), self.d_cap, self.color.data_ptr(),
+                                        self.depth.data_ptr(), self.alpha.data_ptr(), st)
+                _lib.check(rc, "gsb_render_fwd")
+                return self
             rc = lib.gsb_forward(C.byref(self.s), P, K, _ptr(means3D), _ptr(scales), _ptr(rotations),
                                  _ptr(opacities), _ptr(shs), _ptr(colors), _ptr(cov3D), self.radii.data_ptr(),
                                  self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
@@ -415,6 +435,16 @@ def set_blend_variant(name: str) -> None:
 
 
 _pbwd_group = int(__import__("os").environ.get("GSB_PBWD_GROUP", "8"))
+
+
+_fwd_stagger = int(__import__("os").environ.get("GSB_FWD_STAGGER", "0"))
+
+
+def set_forward_stagger(k: int) -> None:
+    """rasterize_views forward on side streams: 0 = all views start together; k > 0 = view v starts its
+    per-Gaussian + binning stages when view v - k has finished binning (so they overlap that view's blend)."""
+    global _fwd_stagger
+    _fwd_stagger = max(0, int(k))
 
 
 def set_backward_grouping(views_per_launch: int) -> None:
@@ -699,10 +729,19 @@ class _RasterizeViews(torch.autograd.Function):
                 calls = []
                 for v in range(v0, min(V, v0 + MAX_SIDE_STREAMS)):
                     with torch.cuda.stream(streams[v]):
-                        calls.append(_ForwardCall(settings_list[v], means3D, sh, colors_precomp, opacities, scales,
-                                                  rotations, cov3Ds_precomp,
-                                                  out=(color[v], radii[v], depth[v], alpha[v]), raw=raw,
-                                                  tanfov_dev=tf(v), forward_only=fo).enqueue())
+                        call = _ForwardCall(settings_list[v], means3D, sh, colors_precomp, opacities, scales,
+                                            rotations, cov3Ds_precomp,
+                                            out=(color[v], radii[v], depth[v], alpha[v]), raw=raw,
+                                            tanfov_dev=tf(v), forward_only=fo)
+                        if _fwd_stagger > 0:
+                            # Staggered start: view v's per-Gaussian + binning stages (latency-bound, they leave most
+                            # of the machine idle) begin when view v - k's binning is done, i.e. they run UNDER that
+                            # view's blend (issue-bound) instead of in lockstep with the other views' binning.
+                            call.mark_binned = True
+                            j = len(calls) - _fwd_stagger
+                            if j >= 0 and calls[j].binned is not None:
+                                streams[v].wait_event(calls[j].binned)
+                        calls.append(call.enqueue())
                 for call in calls:
                     svs.append(call.finish()[4])
             for st in set(streams):
