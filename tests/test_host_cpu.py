@@ -179,3 +179,51 @@ def test_batched_camera_builder_equals_camera():
         assert b.FoVx == ref.FoVx and b.tanfovx == ref.tanfovx and b.image_width == 128
         for name in ("world_view_transform", "projection_matrix", "full_proj_transform", "camera_center"):
             assert torch.equal(getattr(b, name), getattr(ref, name)), name
+
+
+def test_camera_block_rows_equal_camera_objects():
+    """cameras.CameraBlock (fixed-address camera rows for captured steps) holds exactly what Camera(c2w, fovy, H, W)
+    computes, including the device copy of the intrinsics the kernels read when a step is replayed from a CUDA
+    graph; update() rewrites the same tensors in place."""
+    import math
+    import numpy as np
+    from gaussianip_b200.cameras import Camera, CameraBlock, look_at_c2w, orbit_position
+    H, W = 96, 160
+    block = CameraBlock(3, H, W, device="cpu")
+    ptrs = [(c.world_view_transform.data_ptr(), c.full_proj_transform.data_ptr(), c.tanfov_dev.data_ptr())
+            for c in block.cameras]
+    for seed in (0, 1):
+        rng = np.random.default_rng(seed)
+        c2ws = [look_at_c2w(orbit_position(rng.uniform(-180, 180), rng.uniform(-30, 30), rng.uniform(1.3, 1.7)))
+                for _ in range(3)]
+        fovs = [math.radians(rng.uniform(40, 70)) for _ in range(3)]
+        cams = block.update(c2ws, fovs)
+        assert [(c.world_view_transform.data_ptr(), c.full_proj_transform.data_ptr(), c.tanfov_dev.data_ptr())
+                for c in cams] == ptrs                                   # same addresses after every update
+        for cam, c2w, fovy in zip(cams, c2ws, fovs):
+            ref = Camera(c2w, fovy, H, W, data_device="cpu")
+            assert torch.equal(cam.world_view_transform, ref.world_view_transform)
+            assert torch.equal(cam.full_proj_transform, ref.full_proj_transform)
+            assert torch.equal(cam.projection_matrix, ref.projection_matrix)
+            assert torch.equal(cam.camera_center, ref.camera_center)
+            assert cam.FoVx == ref.FoVx and cam.FoVy == ref.FoVy
+            want = torch.tensor([math.tan(ref.FoVx * 0.5), math.tan(ref.FoVy * 0.5)], dtype=torch.float32)
+            assert torch.equal(cam.tanfov_dev, want)
+    with pytest.raises(ValueError):
+        block.update(c2ws[:2], fovs[:2])
+
+
+def test_speculation_capture_hands_out_pinned_count_rows():
+    """graph.CapturedStep gives every captured forward its own row of a pinned pool (allocated before the capture)."""
+    from gaussianip_b200 import rasterizer as R
+    pool = torch.zeros(3, 8, dtype=torch.int32)
+    spec = R.speculation(capture=True, counts_pool=pool)
+    a, b = spec.take_counts(), spec.take_counts()
+    assert a.data_ptr() == pool[0].data_ptr() and b.data_ptr() == pool[1].data_ptr()
+    c = spec.take_counts()
+    assert c.shape == (8,) and c.data_ptr() == pool[2].data_ptr()
+    with pytest.raises(RuntimeError):
+        spec.take_counts()
+    with R.speculation():
+        with pytest.raises(RuntimeError):
+            R.speculation().__enter__()                                   # contexts do not nest
