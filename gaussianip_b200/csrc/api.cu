@@ -96,7 +96,7 @@ static int layout(int P, int H, int W, long long D_cap, GsbLayout* L) {
   L->off_didx0 = take(Pz * 4);
   L->off_didx1 = take(Pz * 4);
   L->off_offsets = take(Pz * 4);
-  L->off_blocksums = take((Pz / 2048 + 2) * 4);
+  L->off_blocksums = take((Pz / 512 + Pz / 16384 + 8) * 8);   // scan chain of the emission kernel (u64 words)
   const size_t nmax = Dz > Pz ? Dz : Pz;
   L->off_hist = take(radix_tmp_bytes((long long)nmax));
   L->off_tkeys0 = take(Dz * 4);

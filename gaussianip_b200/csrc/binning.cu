@@ -84,23 +84,66 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- radix sort -----------------------------------------------------------------------------
-// "Onesweep" organisation: ONE pass over the keys builds the global digit histograms of every
-// pass (they do not depend on the arrangement), then each pass is a single kernel that reads
-// its keys once and writes them once.  A block learns how many keys of each digit precede it
-// from the blocks before it by decoupled look-back over one 32-bit status word per (block,
-// digit): [31:30] = flag (0 not ready, 1 block aggregate, 2 inclusive prefix), [29:0] = count.
-// Block ids are handed out by an atomic counter in arrival order, so a block only ever waits
-// for blocks that are already running.  Stability: the in-block rank follows the original
-// order (warps own consecutive segments, rounds and lanes ascend), blocks are ordered by id.
+// "Onesweep" organisation: the global digit histogram of a pass does not depend on the arrangement of the keys,
+// so it is counted by whoever holds the keys in registers before the pass (the producing kernel for digit 0, the
+// previous pass for the others), and each pass is a single kernel that reads its keys once and writes them once.
+// A block learns how many keys of each digit precede it from the blocks before it through one 32-bit status word
+// per (block, digit): bit 30 = published, [29:0] = count.  Block ids are handed out by an atomic counter in
+// arrival order, so a block only ever waits for blocks that are already running.  Stability: the in-block rank
+// follows the original order (warps own consecutive segments, rounds and lanes ascend), blocks are ordered by id.
+//
+// TWO-LEVEL look-back.  At the sizes of this path (1-2 M keys) all blocks of a pass are co-resident and finish
+// ranking at about the same time, so the classic chained look-back (read a few predecessors, stop at the first
+// inclusive prefix) degenerates into a wavefront that needs ~sqrt(blocks/2) dependent L2 round trips — 8.4 trips
+// per warp on average, 30 % of the executed instructions and half of the stall samples of a pass (ncu r2l).
+// Here blocks form groups of LB_GROUP: a block sums the AGGREGATES of the predecessors inside its group (they are
+// published right after ranking; up to LB_GROUP-1 independent loads), the last block of a group publishes the
+// group's aggregate, and every block adds the aggregates of the groups before its own.  Two dependent waits, a
+// bounded number of loads, nothing spins while it makes progress.
 
-constexpr uint32_t ST_AGG = 1u << 30, ST_PREFIX = 2u << 30, ST_MASK = (1u << 30) - 1;
+constexpr uint32_t ST_READY = 1u << 30, ST_MASK = (1u << 30) - 1;
 constexpr int MAX_PASSES = 8;
-// All blocks of a 1-2 M key pass are co-resident (one wave), so the inclusive prefix travels
-// down the chain of blocks one look-back round trip at a time: read LB predecessors per trip.
+constexpr int LB_GROUP = 32;        // blocks per look-back group
 #ifndef GSB_RADIX_LB
-#define GSB_RADIX_LB 4
+#define GSB_RADIX_LB 16
 #endif
-constexpr int LB = GSB_RADIX_LB;
+constexpr int LB = GSB_RADIX_LB;    // status words requested per L2 round trip
+#ifndef GSB_RADIX_POLL_NS
+#define GSB_RADIX_POLL_NS 100
+#endif
+
+__host__ __device__ inline long long radix_blocks(long long n_cap) { return (n_cap + RS_TILE - 1) / RS_TILE; }
+__host__ __device__ inline long long radix_groups(long long nb) { return (nb + LB_GROUP - 1) / LB_GROUP; }
+
+// Status words are written and polled with gpu-scope relaxed accesses (flag and payload share the word, so no
+// ordering between accesses is needed; `volatile` would compile to system-scope STRONG.SYS accesses).
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Sum of `count` published status words base[0], base[stride], ... (spins on the ones not published yet).
+__device__ __forceinline__ uint32_t sum_published(const uint32_t* base, int count, size_t stride) {
+  uint32_t sum = 0;
+  for (int k0 = 0; k0 < count; k0 += LB) {
+    uint32_t v[LB];
+#pragma unroll
+    for (int k = 0; k < LB; ++k) v[k] = (k0 + k < count) ? ld_status(base + (size_t)(k0 + k) * stride) : ST_READY;
+#pragma unroll
+    for (int k = 0; k < LB; ++k) {
+      while (!(v[k] & ST_READY)) {         // not published yet: yield the issue slots to the blocks still ranking
+        __nanosleep(GSB_RADIX_POLL_NS);
+        v[k] = ld_status(base + (size_t)(k0 + k) * stride);
+      }
+      sum += v[k] & ST_MASK;
+    }
+  }
+  return sum;
+}
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -138,20 +181,38 @@ radix_global_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restri
   }
 }
 
+// Diagnostic build only (-DGSB_RADIX_TIMING): per-block clock64 stamps at the phase boundaries of a pass.
+#ifdef GSB_RADIX_TIMING
+__device__ long long g_radix_timing[8 * 8192];
+#define RS_STAMP(k) do { if (tid == 0 && bid < 8192u) g_radix_timing[bid * 8 + (k)] = clock64(); } while (0)
+#else
+#define RS_STAMP(k) do { } while (0)
+#endif
+
 template <typename KeyT>
 constexpr size_t onesweep_smem_bytes() {
   return (size_t)RS_TILE * (sizeof(KeyT) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + RS_WARPS + 4 + 256) * sizeof(uint32_t);
 }
 
-template <typename KeyT, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS)
+// RANGES (last pass of a tile sort): the pass that puts the instances into their final order also records where
+// every tile's list starts and ends.  In the block-sorted tile equal tile ids are adjacent (the input of the last
+// pass is ordered by all lower bits, and the partition by the top digit is stable), so the first / last key of
+// every run of equal tiles sends its output position to ranges[tile] with one atomic: x accumulates the maximum
+// of ~position (= the minimum position; the array starts zeroed), y the maximum of position + 1.
+// tile_order_kernel decodes x and resets empty tiles to (0, 0).
+#ifndef GSB_RADIX_MINB
+#define GSB_RADIX_MINB 4
+#endif
+template <typename KeyT, bool IOTA, bool RANGES>
+__global__ void __launch_bounds__(RS_THREADS, GSB_RADIX_MINB)
 radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                       const uint32_t* __restrict__ d_n, long long n_cap, int shift,
                       const uint32_t* __restrict__ ghist /*[256] of this pass*/,
                       uint32_t* __restrict__ ghist_next /*[256] of the next pass, or null*/,
-                      volatile uint32_t* __restrict__ status /*[num_blocks][256] of this pass*/,
-                      uint32_t* __restrict__ block_counter) {
+                      uint32_t* __restrict__ status /*[num_blocks][256] of this pass*/,
+                      uint32_t* __restrict__ gstatus /*[num_groups][256] of this pass*/,
+                      uint32_t* __restrict__ block_counter, uint2* __restrict__ ranges) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);                         // block-sorted keys
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + RS_TILE);
@@ -173,6 +234,10 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
   const long long block_base = (long long)bid * RS_TILE;
   if (block_base >= n) return;
   const int count = (int)((n - block_base) < (long long)RS_TILE ? (n - block_base) : (long long)RS_TILE);
+  RS_STAMP(0);
+#ifdef GSB_RADIX_TIMING
+  if (tid == 0 && bid < 8192u) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_radix_timing[bid * 8 + 7] = gt; }
+#endif
 
   KeyT key[RS_IPT];
   uint32_t val[RS_IPT];
@@ -193,6 +258,7 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
     for (int r = 0; r < RS_IPT; ++r)
       if (seg + r * 32 + lane < n) atomicAdd(&s_hn[digit_of(key[r], shift + 8)], 1u);
   }
+  RS_STAMP(1);
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     const long long idx = seg + r * 32 + lane;
@@ -209,54 +275,27 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
     rank[r] = old + (uint32_t)__popc(peers & lt);
     __syncwarp();
   }
+  RS_STAMP(2);
   __syncthreads();
-  {
-    // thread tid owns digit tid: exclusive offsets of the warps inside the block, block count
-    uint32_t run = 0;
+  RS_STAMP(3);
+  // thread tid owns digit tid: exclusive offsets of the warps inside the block, block count
+  uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      const uint32_t c = s_cnt[w][tid];
-      s_cnt[w][tid] = run;
-      run += c;
-    }
-    volatile uint32_t* mine = status + (size_t)bid * 256 + tid;
-    uint32_t excl = 0;
-    if (bid == 0) {
-      *mine = ST_PREFIX | run;
-    } else {
-      *mine = ST_AGG | run;
-      long long j = (long long)bid - 1;
-      bool found = false;
-      while (!found) {                           // LB predecessors per L2 round trip
-        uint32_t v[LB];
-#pragma unroll
-        for (int k = 0; k < LB; ++k) {
-          v[k] = 2u << 30;                       // virtual block -1: inclusive prefix 0
-          if (j - k >= 0) v[k] = status[(size_t)(j - k) * 256 + tid];
-        }
-        int used = 0;
-#pragma unroll
-        for (int k = 0; k < LB; ++k) {
-          if (found || used != k) continue;
-          const uint32_t flag = v[k] & ~ST_MASK;
-          if (flag == 0) continue;               // running but not published yet: retry from here
-          excl += v[k] & ST_MASK;
-          used = k + 1;
-          if (flag == ST_PREFIX) found = true;
-        }
-        j -= used;
-      }
-      *mine = ST_PREFIX | (excl + run);
-    }
-    // position of this digit's run inside the block-sorted tile
-    const uint32_t local = block_exclusive_scan_256(run, s_warp, nullptr);   // syncs inside
-    s_goff[tid] = dbase + excl - local;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][tid] += local;
+  for (int w = 0; w < RS_WARPS; ++w) {
+    const uint32_t c = s_cnt[w][tid];
+    s_cnt[w][tid] = run;
+    run += c;
   }
+  const uint32_t j = bid % LB_GROUP, g = bid / LB_GROUP;
+  st_status(status + (size_t)bid * 256 + tid, ST_READY | run);   // this block's aggregate: nothing else is needed from it
+  // position of this digit's run inside the block-sorted tile
+  const uint32_t local = block_exclusive_scan_256(run, s_warp, nullptr);   // syncs inside
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][tid] += local;
   __syncthreads();
-  // stage the tile in shared memory in sorted order, then write runs of equal digits with
-  // consecutive threads -> consecutive addresses (coalesced instead of one sector per key)
+  // stage the tile in shared memory in sorted order (needs only block-local offsets), so that the wait for the
+  // predecessors below overlaps with it; runs of equal digits are then written by consecutive threads ->
+  // consecutive addresses (coalesced instead of one sector per key)
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     const long long idx = seg + r * 32 + lane;
@@ -266,94 +305,130 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
       s_vals[lpos] = val[r];
     }
   }
+  RS_STAMP(4);
+  {
+    // two-level look-back (see the header of this section): aggregates of the predecessors inside my group,
+    // then aggregates of the groups before mine.  A digit this block holds no key of needs no offset; only the
+    // last block of a group must sum every digit, because it publishes the group's aggregate.
+    const bool leader = j == LB_GROUP - 1;
+    uint32_t excl = 0;
+    if (run != 0u || leader) {
+      excl = sum_published(status + (size_t)(bid - j) * 256 + tid, (int)j, 256);
+      if (leader) st_status(gstatus + (size_t)g * 256 + tid, ST_READY | (excl + run));
+      if (run != 0u) excl += sum_published(gstatus + tid, (int)g, 256);
+    }
+    s_goff[tid] = dbase + excl - local;
+  }
   __syncthreads();
+  RS_STAMP(5);
   for (int i = tid; i < count; i += RS_THREADS) {
     const KeyT k = s_keys[i];
     const uint32_t pos = s_goff[digit_of(k, shift)] + (uint32_t)i;
     keys_out[pos] = k;
     vals_out[pos] = s_vals[i];
+    if (RANGES) {
+      constexpr int tsh = sizeof(KeyT) == 8 ? 32 : 0;
+      const uint32_t t = (uint32_t)(k >> tsh);
+      if (i == 0 || (uint32_t)(s_keys[i - 1] >> tsh) != t) atomicMax(&ranges[t].x, ~pos);
+      if (i == count - 1 || (uint32_t)(s_keys[i + 1] >> tsh) != t) atomicMax(&ranges[t].y, pos + 1u);
+    }
   }
   if (ghist_next && s_hn[tid]) atomicAdd(&ghist_next[tid], s_hn[tid]);   // ordered by the barrier above
+  RS_STAMP(6);
 }
 
 // ---- scan of tiles_touched (gathered through an order) + instance emission -------------------
 
-constexpr int SC_IPT = 8;
-constexpr int SC_TILE = RS_THREADS * SC_IPT;  // 2048 Gaussians per block
+#ifndef GSB_EMIT_IPT
+#define GSB_EMIT_IPT 4
+#endif
+constexpr int SC_IPT = GSB_EMIT_IPT;
+constexpr int SC_TILE = RS_THREADS * SC_IPT;  // Gaussians per block
+static_assert(SC_TILE >= 512, "GsbLayout.off_blocksums is sized for >= 512 Gaussians per block");
 
-__global__ void __launch_bounds__(RS_THREADS)
-tiles_partial_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order, int P,
-                     uint32_t* __restrict__ blocksums) {
-  __shared__ uint32_t s_warp[RS_WARPS];
-  const int base = blockIdx.x * SC_TILE;
-  uint32_t sum = 0;
-#pragma unroll
-  for (int k = 0; k < SC_IPT; ++k) {
-    const int j = base + k * RS_THREADS + threadIdx.x;
-    if (j < P) sum += tiles[order ? order[j] : j];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < RS_WARPS; ++w) t += s_warp[w];
-    blocksums[blockIdx.x] = t;
-  }
-}
+// Scan chain of the emission kernel (one 64-bit word per block and per group of LB_GROUP blocks, bit 63 =
+// published; word 0 = the ticket counter, word 1 = the parked prefiltered flag).  Same two-level scheme as the radix look-back, one value per block.
+constexpr unsigned long long CH_READY = 1ull << 63;
+__host__ __device__ inline size_t emit_chain_words(long long blocks) { return (size_t)(2 + blocks + radix_groups(blocks)); }
 
-// single block: exclusive scan of the per-block sums; publishes D and the overflow flag
-__global__ void __launch_bounds__(RS_THREADS)
-scan_blocksums_kernel(uint32_t* __restrict__ blocksums, int num_blocks, uint32_t* __restrict__ counts,
-                      long long D_cap, int mode, const uint32_t* __restrict__ flag_word) {
-  __shared__ uint32_t s_warp[RS_WARPS];
-  unsigned long long carry = 0;
-  for (int base = 0; base < num_blocks; base += RS_THREADS) {
-    const int i = base + threadIdx.x;
-    const uint32_t v = i < num_blocks ? blocksums[i] : 0;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan_256(v, s_warp, &total);
-    if (i < num_blocks) blocksums[i] = (uint32_t)carry + ex;
-    carry += total;
-  }
-  if (threadIdx.x == 0) {
-    const unsigned long long D = carry;
-    counts[CNT_D] = D > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)D;
-    counts[CNT_OVERFLOW] = D > (unsigned long long)D_cap ? 1u : 0u;
-    counts[CNT_VISIBLE] = 0; counts[CNT_MAXTILES] = 0;   // reserved; the whole block is copied to the host
-    counts[4] = (uint32_t)mode;
-    counts[CNT_PREFILTER] = *flag_word;     // points culled although the caller declared them prefiltered
-    counts[6] = 0; counts[7] = 0;
-  }
-}
-
+// Offsets + instance emission in ONE kernel.  A block gathers tiles_touched of its Gaussians through the
+// emission order, scans them, learns the number of instances before it from the scan chain (blocks take tickets in
+// arrival order; warp 0 sums the published totals of the predecessors in its group and of the earlier groups, 32
+// words per round trip) and writes its instances.  The block holding the last ticket publishes D, the overflow
+// flag and the rest of the counts row.  (Round 1 ran a partial-sum kernel, a one-block scan and this kernel.)
 // MODE 0: write (tile id, Gaussian id) ; MODE 1: write (tile<<32|depth, Gaussian id)
 template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS)
 emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order, int P,
-            const uint32_t* __restrict__ blocksums, const ushort4* __restrict__ rect,
+            volatile unsigned long long* __restrict__ chain, int num_blocks, const ushort4* __restrict__ rect,
             const uint32_t* __restrict__ dkeys, int gx, long long D_cap, uint32_t* __restrict__ tkeys,
-            uint64_t* __restrict__ keys64, uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist0) {
+            uint64_t* __restrict__ keys64, uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist0,
+            uint32_t* __restrict__ counts, int mode, const uint32_t* __restrict__ flag_word) {
   __shared__ uint32_t s_warp[RS_WARPS];
   __shared__ uint32_t s_h0[256];     // digit-0 histogram of the emitted keys (first pass of the sort)
+  __shared__ uint32_t s_bid, s_base;
+  if (threadIdx.x == 0) s_bid = (uint32_t)atomicAdd(const_cast<unsigned long long*>(chain), 1ull);
   s_h0[threadIdx.x] = 0;
   __syncthreads();
+  const int bid = (int)s_bid;
   // blocked arrangement: thread t owns SC_IPT consecutive Gaussians of the emission order
-  const int first = blockIdx.x * SC_TILE + threadIdx.x * SC_IPT;
+  const int first = bid * SC_TILE + threadIdx.x * SC_IPT;
   uint32_t gid[SC_IPT], cnt[SC_IPT];
   uint32_t mine = 0;
 #pragma unroll
   for (int k = 0; k < SC_IPT; ++k) {
     const int j = first + k;
-    gid[k] = 0; cnt[k] = 0;
-    if (j < P) {
-      gid[k] = order ? order[j] : (uint32_t)j;
-      cnt[k] = tiles[gid[k]];
-    }
+    gid[k] = 0;
+    if (j < P) gid[k] = order ? order[j] : (uint32_t)j;
+  }
+#pragma unroll
+  for (int k = 0; k < SC_IPT; ++k) {
+    cnt[k] = (first + k < P) ? tiles[gid[k]] : 0u;
     mine += cnt[k];
   }
-  uint32_t off = blocksums[blockIdx.x] + block_exclusive_scan_256(mine, s_warp, nullptr);
+  uint32_t total;
+  const uint32_t ex = block_exclusive_scan_256(mine, s_warp, &total);     // syncs inside
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    volatile unsigned long long* bst = chain + 2;
+    volatile unsigned long long* gst = bst + num_blocks;
+    const int j = bid % LB_GROUP, g = bid / LB_GROUP;
+    if (lane == 0) bst[bid] = CH_READY | (unsigned long long)total;
+    unsigned long long sum = 0;
+    if (lane < j) {
+      unsigned long long v;
+      do { v = bst[bid - j + lane]; } while (!(v & CH_READY));
+      sum = v & ~CH_READY;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (j == LB_GROUP - 1 && lane == 0) gst[g] = CH_READY | (sum + total);
+    unsigned long long gsum = 0;
+    for (int k0 = 0; k0 < g; k0 += 32) {
+      if (k0 + lane < g) {
+        unsigned long long v;
+        do { v = gst[k0 + lane]; } while (!(v & CH_READY));
+        gsum += v & ~CH_READY;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+    const unsigned long long base = sum + gsum;
+    if (lane == 0) {
+      s_base = (uint32_t)base;
+      if (bid == num_blocks - 1) {
+        const unsigned long long D = base + total;
+        counts[CNT_D] = D > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)D;
+        counts[CNT_OVERFLOW] = D > (unsigned long long)D_cap ? 1u : 0u;
+        counts[CNT_VISIBLE] = 0; counts[CNT_MAXTILES] = 0;   // reserved; the whole row is copied to the host
+        counts[4] = (uint32_t)mode;
+        counts[CNT_PREFILTER] = *flag_word;     // points culled although the caller declared them prefiltered
+        counts[6] = 0; counts[7] = 0;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t off = s_base + ex;
   constexpr uint32_t BIG = 64;   // splats touching more tiles than this are emitted by the whole warp
   uint32_t offk[SC_IPT];
 #pragma unroll
@@ -418,13 +493,19 @@ __global__ void tile_ranges_kernel(const KeyT* __restrict__ keys, const uint32_t
 
 // Heaviest-first CTA order for the blend kernels: tiles bucketed by floor(log2(list length)),
 // longest bucket first (order inside a bucket is irrelevant: it only affects scheduling).
+// `encoded`: ranges come from the RANGES pass of the sort (x = ~start, untouched tiles all zero) and are decoded
+// in place first, so that every consumer sees the reference's values (start, end; (0, 0) for an empty tile).
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const uint2* __restrict__ ranges, int T, uint32_t* __restrict__ order) {
+tile_order_kernel(uint2* __restrict__ ranges, int T, uint32_t* __restrict__ order, int encoded) {
   __shared__ uint32_t s_cnt[33], s_cur[33];
   if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const uint2 r = ranges[t];
+    uint2 r = ranges[t];
+    if (encoded) {
+      r = r.y == 0u ? make_uint2(0u, 0u) : make_uint2(~r.x, r.y);
+      ranges[t] = r;                      // re-read below by the same thread
+    }
     atomicAdd(&s_cnt[32 - __clz(r.y - r.x)], 1u);
   }
   __syncthreads();
@@ -460,15 +541,17 @@ int radix_num_passes(int end_bit) { return (end_bit + 7) / 8; }
 bool radix_result_in_A(int passes) { return (passes & 1) != 0; }
 
 // tmp layout: [MAX_PASSES][256] global histograms | [MAX_PASSES] block counters (padded to 256) |
-//             [MAX_PASSES][num_blocks][256] look-back status words
+//             [MAX_PASSES][num_blocks + num_groups][256] look-back status words (blocks, then groups)
+static size_t radix_status_words(long long n_cap) {
+  const long long nb = radix_blocks(n_cap > 0 ? n_cap : 1);
+  return (size_t)(nb + radix_groups(nb)) * 256;
+}
 size_t radix_tmp_bytes(long long n_cap) {
-  const long long nb = (n_cap + RS_TILE - 1) / RS_TILE;
-  return (size_t)(MAX_PASSES * 256 + 256 + (size_t)MAX_PASSES * (nb > 0 ? nb : 1) * 256) * sizeof(uint32_t);
+  return (size_t)(MAX_PASSES * 256 + 256 + (size_t)MAX_PASSES * radix_status_words(n_cap)) * sizeof(uint32_t);
 }
 
 static size_t radix_used_bytes(long long n_cap, int passes) {
-  const long long nb = (n_cap + RS_TILE - 1) / RS_TILE;
-  return (size_t)(MAX_PASSES * 256 + 256 + (size_t)passes * (nb > 0 ? nb : 1) * 256) * sizeof(uint32_t);
+  return (size_t)(MAX_PASSES * 256 + 256 + (size_t)passes * radix_status_words(n_cap)) * sizeof(uint32_t);
 }
 
 // Zero the histograms / counters / look-back words of one sort.  Must run BEFORE the kernel that
@@ -481,7 +564,7 @@ int radix_prepare(long long n_cap, int end_bit, void* tmp, cudaStream_t st) {
 
 uint32_t* radix_hist0(void* tmp) { return static_cast<uint32_t*>(tmp); }
 // A spare word of the (zeroed) counter row: preprocess_fwd raises it when GsbSettings.prefiltered is set and a point
-// fails the near-plane test; scan_blocksums publishes it as counts[5].
+// fails the near-plane test; the emission kernel publishes it as counts[5].
 uint32_t* radix_flag_word(void* tmp) { return static_cast<uint32_t*>(tmp) + MAX_PASSES * 256 + 255; }
 
 // Stable LSD sort on bits [0,end_bit).  Pass 0 reads (src_keys, src_vals); pass p writes
@@ -493,7 +576,7 @@ uint32_t* radix_flag_word(void* tmp) { return static_cast<uint32_t*>(tmp) + MAX_
 template <typename KeyT>
 int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys, const uint32_t* src_vals,
                      KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
-                     bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st) {
+                     bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st, uint2* ranges) {
   if (n_cap <= 0) return GSB_OK;
   const int passes = radix_num_passes(end_bit);
   if (passes == 0) return GSB_OK;
@@ -508,10 +591,12 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
     int dev = 0;
     GSB_CUDA(cudaGetDevice(&dev));
     if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
-      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, true, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, false, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GSB_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, false, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
   }
@@ -526,23 +611,29 @@ int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys,
     const uint32_t* vin = p == 0 ? src_vals : ((p & 1) ? valsA : valsB);
     KeyT* kout = (p & 1) ? keysB : keysA;
     uint32_t* vout = (p & 1) ? valsB : valsA;
-    uint32_t* stp = status + (size_t)p * nb * 256;
+    uint32_t* stp = status + (size_t)p * radix_status_words(n_cap);
+    uint32_t* gstp = stp + (size_t)nb * 256;
     uint32_t* gnext = p + 1 < passes ? ghist + (p + 1) * 256 : nullptr;
     if (p == 0 && iota_vals)
-      radix_onesweep_kernel<KeyT, true><<<nb, RS_THREADS, smem, st>>>(kin, vin, kout, vout, d_n, n_cap, 8 * p,
-                                                                      ghist + p * 256, gnext, stp, counters + p);
+      radix_onesweep_kernel<KeyT, true, false><<<nb, RS_THREADS, smem, st>>>(
+          kin, vin, kout, vout, d_n, n_cap, 8 * p, ghist + p * 256, gnext, stp, gstp, counters + p, nullptr);
+    else if (p == passes - 1 && ranges)
+      radix_onesweep_kernel<KeyT, false, true><<<nb, RS_THREADS, smem, st>>>(
+          kin, vin, kout, vout, d_n, n_cap, 8 * p, ghist + p * 256, gnext, stp, gstp, counters + p, ranges);
     else
-      radix_onesweep_kernel<KeyT, false><<<nb, RS_THREADS, smem, st>>>(kin, vin, kout, vout, d_n, n_cap, 8 * p,
-                                                                       ghist + p * 256, gnext, stp, counters + p);
+      radix_onesweep_kernel<KeyT, false, false><<<nb, RS_THREADS, smem, st>>>(
+          kin, vin, kout, vout, d_n, n_cap, 8 * p, ghist + p * 256, gnext, stp, gstp, counters + p, nullptr);
     GSB_POST_LAUNCH(debug, st, "radix_onesweep_kernel");
   }
   return GSB_OK;
 }
 
 template int radix_sort_pairs<uint32_t>(long long, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*,
-                                        uint32_t*, uint32_t*, uint32_t*, int, bool, bool, void*, bool, cudaStream_t);
+                                        uint32_t*, uint32_t*, uint32_t*, int, bool, bool, void*, bool, cudaStream_t,
+                                        uint2*);
 template int radix_sort_pairs<uint64_t>(long long, const uint32_t*, const uint64_t*, const uint32_t*, uint64_t*,
-                                        uint32_t*, uint64_t*, uint32_t*, int, bool, bool, void*, bool, cudaStream_t);
+                                        uint32_t*, uint64_t*, uint32_t*, int, bool, bool, void*, bool, cudaStream_t,
+                                        uint2*);
 
 int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbLayout& L,
                     long long D_cap, int mode, uint32_t* host_counts, cudaEvent_t event, bool debug,
@@ -553,9 +644,10 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   const ushort4* rect = at<ushort4>(scratch, L.off_rect);
   const uint32_t* tiles = at<uint32_t>(scratch, L.off_tiles);
   const uint32_t* dkeys = at<uint32_t>(scratch, L.off_dkeys0);   // written by preprocess, kept intact
-  uint32_t* blocksums = at<uint32_t>(scratch, L.off_blocksums);
+  unsigned long long* chain = at<unsigned long long>(scratch, L.off_blocksums);
   void* hist = at<char>(scratch, L.off_hist);
   const int T = v.gx * v.gy;
+  if (mode != GSB_BIN_TWO_LEVEL && mode != GSB_BIN_FLAT64) return GSB_E_INVALID;
   GSB_CUDA(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), st));
   auto publish = [&]() -> int {
     if (host_counts)
@@ -565,7 +657,7 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   };
   if (P == 0) {
     GSB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(uint32_t), st));
-    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order));
+    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order), 0);
     GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
     return publish();
   }
@@ -573,9 +665,11 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   const int tile_bits = bits_for((unsigned)(T - 1));
   const int cap_blocks = (int)((D_cap + 255) / 256);
   uint32_t* alt_vals = at<uint32_t>(scratch, L.off_tvals_alt);
+  const bool two_level = mode == GSB_BIN_TWO_LEVEL;
   int rc;
 
-  if (mode == GSB_BIN_TWO_LEVEL) {
+  const uint32_t* order = nullptr;
+  if (two_level) {
     // (1) Gaussians by depth key (ties by index: the sort is stable and values start as iota)
     uint32_t* kA = at<uint32_t>(scratch, L.off_dkeys1);
     uint32_t* vA = at<uint32_t>(scratch, L.off_didx0);
@@ -583,72 +677,60 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
     uint32_t* vB = at<uint32_t>(scratch, L.off_didx1);
     prof_begin(GSB_STAGE_DEPTH_SORT, st);
     // digit-0 histogram of the depth keys was accumulated by preprocess_fwd (after radix_prepare)
-    rc = radix_sort_pairs<uint32_t>(P, nullptr, dkeys, nullptr, kA, vA, kB, vB, 32, true, true, hist, debug, st);
+    rc = radix_sort_pairs<uint32_t>(P, nullptr, dkeys, nullptr, kA, vA, kB, vB, 32, true, true, hist, debug, st,
+                                    nullptr);
     prof_end(GSB_STAGE_DEPTH_SORT, st);
     if (rc) return rc;
-    prof_begin(GSB_STAGE_SCAN_EMIT, st);
-    const uint32_t* order = vB;  // 4 passes -> result in B
-    // (2) offsets in that order, D, overflow flag
-    tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums);
-    GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
-    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode, radix_flag_word(hist));
-    GSB_POST_LAUNCH(debug, st, "scan_blocksums_kernel");
-    if ((rc = publish())) return rc;
-    // (3) emit (tile id, Gaussian id) in (depth, id, tile) order, then stable partition by tile
-    const bool inA = radix_result_in_A(radix_num_passes(tile_bits));
-    uint32_t* tkA = at<uint32_t>(scratch, L.off_tkeys0);
-    uint32_t* tkB = at<uint32_t>(scratch, L.off_tkeys1);
-    uint32_t* tvA = inA ? point_list : alt_vals;
-    uint32_t* tvB = inA ? alt_vals : point_list;
-    if ((rc = radix_prepare(D_cap, tile_bits, hist, st))) return rc;
-    emit_kernel<0><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, blocksums, rect, dkeys, v.gx, D_cap, tkB,
-                                                     nullptr, tvB, radix_hist0(hist));
-    GSB_POST_LAUNCH(debug, st, "emit_kernel");
-    prof_end(GSB_STAGE_SCAN_EMIT, st);
-    prof_begin(GSB_STAGE_TILE_SORT, st);
-    rc = radix_sort_pairs<uint32_t>(D_cap, counts + CNT_D, tkB, tvB, tkA, tvA, tkB, tvB, tile_bits, false, true,
-                                    hist, debug, st);
-    prof_end(GSB_STAGE_TILE_SORT, st);
-    if (rc) return rc;
-    ProfScope pr(GSB_STAGE_RANGES, st);
-    // (a single-tile image needs 0 passes: the emitted order in B is already final)
-    tile_ranges_kernel<uint32_t><<<cap_blocks, 256, 0, st>>>(inA ? tkA : tkB, counts + CNT_D, D_cap, ranges);
-    GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
-    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order));
-    GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
-    return GSB_OK;
+    order = vB;  // 4 passes -> result in B
   }
-  if (mode == GSB_BIN_FLAT64) {
-    prof_begin(GSB_STAGE_SCAN_EMIT, st);
-    tiles_partial_kernel<<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums);
-    GSB_POST_LAUNCH(debug, st, "tiles_partial_kernel");
-    scan_blocksums_kernel<<<1, RS_THREADS, 0, st>>>(blocksums, sc_blocks, counts, D_cap, mode, radix_flag_word(hist));
-    GSB_POST_LAUNCH(debug, st, "scan_blocksums_kernel");
-    if ((rc = publish())) return rc;
-    const int end_bit = 32 + tile_bits;
-    const bool inA = radix_result_in_A(radix_num_passes(end_bit));
-    uint64_t* kA = at<uint64_t>(scratch, L.off_keys64_0);
-    uint64_t* kB = at<uint64_t>(scratch, L.off_keys64_1);
-    uint32_t* tvA = inA ? point_list : alt_vals;
-    uint32_t* tvB = inA ? alt_vals : point_list;
-    if ((rc = radix_prepare(D_cap, end_bit, hist, st))) return rc;
-    emit_kernel<1><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, blocksums, rect, dkeys, v.gx, D_cap,
-                                                     nullptr, kB, tvB, radix_hist0(hist));
-    GSB_POST_LAUNCH(debug, st, "emit_kernel");
-    prof_end(GSB_STAGE_SCAN_EMIT, st);
-    prof_begin(GSB_STAGE_TILE_SORT, st);
-    rc = radix_sort_pairs<uint64_t>(D_cap, counts + CNT_D, kB, tvB, kA, tvA, kB, tvB, end_bit, false, true, hist,
-                                    debug, st);
-    prof_end(GSB_STAGE_TILE_SORT, st);
-    if (rc) return rc;
-    ProfScope pr(GSB_STAGE_RANGES, st);
-    tile_ranges_kernel<uint64_t><<<cap_blocks, 256, 0, st>>>(inA ? kA : kB, counts + CNT_D, D_cap, ranges);
+  // (2) offsets in emission order, D, overflow flag and the instances themselves, one kernel.  Two-level mode
+  // emits (tile id, Gaussian id) in (depth, id, tile) order and then partitions stably by tile; flat mode emits
+  // (tile<<32|depth, Gaussian id) in Gaussian order and sorts the 64-bit keys (the reference's structure).
+  prof_begin(GSB_STAGE_SCAN_EMIT, st);
+  const int end_bit = two_level ? tile_bits : 32 + tile_bits;
+  const int passes = radix_num_passes(end_bit);
+  const bool inA = radix_result_in_A(passes);
+  uint32_t* tkA = at<uint32_t>(scratch, L.off_tkeys0);
+  uint32_t* tkB = at<uint32_t>(scratch, L.off_tkeys1);
+  uint64_t* kA64 = at<uint64_t>(scratch, L.off_keys64_0);
+  uint64_t* kB64 = at<uint64_t>(scratch, L.off_keys64_1);
+  uint32_t* tvA = inA ? point_list : alt_vals;
+  uint32_t* tvB = inA ? alt_vals : point_list;
+  GSB_CUDA(cudaMemsetAsync(chain, 0, emit_chain_words(sc_blocks) * sizeof(unsigned long long), st));
+  // the prefiltered-violation flag of preprocess_fwd sits in the sort's counter row, which the next line zeroes
+  // for the tile sort: park it in the spare chain word first
+  GSB_CUDA(cudaMemcpyAsync(chain + 1, radix_flag_word(hist), sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  if ((rc = radix_prepare(D_cap, end_bit, hist, st))) return rc;
+  if (two_level)
+    emit_kernel<0><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, chain, sc_blocks, rect, dkeys, v.gx, D_cap, tkB,
+                                                     nullptr, tvB, radix_hist0(hist), counts, mode,
+                                                     reinterpret_cast<const uint32_t*>(chain + 1));
+  else
+    emit_kernel<1><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, chain, sc_blocks, rect, dkeys, v.gx, D_cap,
+                                                     nullptr, kB64, tvB, radix_hist0(hist), counts, mode,
+                                                     reinterpret_cast<const uint32_t*>(chain + 1));
+  GSB_POST_LAUNCH(debug, st, "emit_kernel");
+  if ((rc = publish())) return rc;
+  prof_end(GSB_STAGE_SCAN_EMIT, st);
+  // (3) the sort; its last pass also writes the tile ranges
+  prof_begin(GSB_STAGE_TILE_SORT, st);
+  if (two_level)
+    rc = radix_sort_pairs<uint32_t>(D_cap, counts + CNT_D, tkB, tvB, tkA, tvA, tkB, tvB, end_bit, false, true, hist,
+                                    debug, st, ranges);
+  else
+    rc = radix_sort_pairs<uint64_t>(D_cap, counts + CNT_D, kB64, tvB, kA64, tvA, kB64, tvB, end_bit, false, true,
+                                    hist, debug, st, ranges);
+  prof_end(GSB_STAGE_TILE_SORT, st);
+  if (rc) return rc;
+  ProfScope pr(GSB_STAGE_RANGES, st);
+  if (passes == 0) {
+    // a single-tile image in two-level mode needs no pass: the emitted order (in B) is already final
+    tile_ranges_kernel<uint32_t><<<cap_blocks, 256, 0, st>>>(tkB, counts + CNT_D, D_cap, ranges);
     GSB_POST_LAUNCH(debug, st, "tile_ranges_kernel");
-    tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order));
-    GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
-    return GSB_OK;
   }
-  return GSB_E_INVALID;
+  tile_order_kernel<<<1, 1024, 0, st>>>(ranges, T, at<uint32_t>(saved, L.off_tile_order), passes > 0 ? 1 : 0);
+  GSB_POST_LAUNCH(debug, st, "tile_order_kernel");
+  return GSB_OK;
 }
 
 int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void* scratch, const GsbLayout& L,
@@ -679,3 +761,9 @@ int launch_debug_sorted_keys(const View& v, int P, const void* saved, const void
 }
 
 }  // namespace gsb
+
+#ifdef GSB_RADIX_TIMING
+extern "C" int gsb_debug_radix_timing(long long* out, int words) {
+  return (int)cudaMemcpyFromSymbol(out, gsb::g_radix_timing, (size_t)words * sizeof(long long));
+}
+#endif

@@ -212,7 +212,8 @@ size_t radix_tmp_bytes(long long n_cap);
 template <typename KeyT>
 int radix_sort_pairs(long long n_cap, const uint32_t* d_n, const KeyT* src_keys, const uint32_t* src_vals,
                      KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, int end_bit,
-                     bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st);
+                     bool iota_vals, bool hist0_ready, void* tmp, bool debug, cudaStream_t st,
+                     uint2* ranges = nullptr);   // ranges: the last pass also writes encoded tile ranges (binning.cu)
 int radix_prepare(long long n_cap, int end_bit, void* tmp, cudaStream_t st);
 uint32_t* radix_hist0(void* tmp);
 uint32_t* radix_flag_word(void* tmp);

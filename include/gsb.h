@@ -94,7 +94,7 @@ typedef struct GsbLayout {
   size_t off_dkeys1, off_dkeys2;   /* P x u32  depth-sort ping/pong keys */
   size_t off_didx0, off_didx1;     /* P x u32  depth-sort ping/pong Gaussian ids */
   size_t off_offsets;     /* P x u32  exclusive scan of tiles_touched in emission order */
-  size_t off_blocksums;   /* scan partials */
+  size_t off_blocksums;   /* scan chain of the emission kernel (u64 words) */
   size_t off_hist;        /* radix per-block digit histograms + digit totals */
   size_t off_tkeys0, off_tkeys1;   /* D_cap x u32 tile ids ping/pong */
   size_t off_tvals_alt;   /* D_cap x u32 */
