@@ -20,7 +20,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_blend_variant{0};
-static std::atomic<int> g_fwd_variant{0};     // 0 per-hit forward blend, 1 transposed (two-phase) forward blend
+static std::atomic<int> g_fwd_variant{0};     // 0 per-hit forward blend (cp.async), 1 transposed (two-phase), 2 per-hit with TMA gather4
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- stage profiler ------------------------------------------------------------------------
@@ -182,8 +182,9 @@ int gsb_adam_step(int n_groups, float* const* params, const float* const* grads,
 }
 
 int gsb_set_blend_variant(int variant) {
-  // 10 / 11 select the forward blend kernel (per-hit / transposed) and leave the backward choice alone
-  if (variant == 10 || variant == 11) { g_fwd_variant.store(variant - 10); return GSB_OK; }
+  // 10 / 11 / 12 select the forward blend kernel (per-hit with cp.async gathers / transposed / per-hit with TMA
+  // gather4 row gathers) and leave the backward choice alone
+  if (variant >= 10 && variant <= 12) { g_fwd_variant.store(variant - 10); return GSB_OK; }
   if (variant < 0 || variant > 4) return GSB_E_INVALID;
   g_blend_variant.store(variant);
   return GSB_OK;
@@ -237,12 +238,12 @@ int gsb_render_fwd(const GsbSettings* s, int P, void* saved, long long D_cap, fl
                               at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T), s->debug != 0,
                               (cudaStream_t)stream);
   const bool record = s->forward_only == 0;
-  return launch_render_fwd(make_view(s), at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
+  return launch_render_fwd(make_view(s), P, at<Geom>(saved, L.off_geom), at<uint32_t>(saved, L.off_point_list),
                            at<uint2>(saved, L.off_ranges), at<uint32_t>(saved, L.off_tile_order), out_color,
                            out_depth, out_alpha,
                            at<uint32_t>(saved, L.off_n_contrib), at<float>(saved, L.off_final_T),
                            record ? at<uint2>(saved, L.off_hits) : nullptr,
-                           record ? at<uint32_t>(saved, L.off_hit_count) : nullptr, g_fwd_variant.load() == 1,
+                           record ? at<uint32_t>(saved, L.off_hit_count) : nullptr, g_fwd_variant.load(),
                            s->debug != 0, (cudaStream_t)stream);
 }
 

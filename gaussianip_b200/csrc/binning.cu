@@ -349,6 +349,14 @@ static_assert(SC_TILE >= 512, "GsbLayout.off_blocksums is sized for >= 512 Gauss
 // Scan chain of the emission kernel (one 64-bit word per block and per group of LB_GROUP blocks, bit 63 =
 // published; word 0 = the ticket counter, word 1 = the parked prefiltered flag).  Same two-level scheme as the radix look-back, one value per block.
 constexpr unsigned long long CH_READY = 1ull << 63;
+__device__ __forceinline__ unsigned long long ld_chain(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_chain(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __host__ __device__ inline size_t emit_chain_words(long long blocks) { return (size_t)(2 + blocks + radix_groups(blocks)); }
 
 // Offsets + instance emission in ONE kernel.  A block gathers tiles_touched of its Gaussians through the
@@ -357,23 +365,31 @@ __host__ __device__ inline size_t emit_chain_words(long long blocks) { return (s
 // words per round trip) and writes its instances.  The block holding the last ticket publishes D, the overflow
 // flag and the rest of the counts row.  (Round 1 ran a partial-sum kernel, a one-block scan and this kernel.)
 // MODE 0: write (tile id, Gaussian id) ; MODE 1: write (tile<<32|depth, Gaussian id)
+#ifndef GSB_EMIT_MINB
+#define GSB_EMIT_MINB 6
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(RS_THREADS)
-emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ order, int P,
-            volatile unsigned long long* __restrict__ chain, int num_blocks, const ushort4* __restrict__ rect,
+__global__ void __launch_bounds__(RS_THREADS, GSB_EMIT_MINB)
+emit_kernel(const uint32_t* __restrict__ order, int P,
+            unsigned long long* __restrict__ chain, int num_blocks, const ushort4* __restrict__ rect,
             const uint32_t* __restrict__ dkeys, int gx, long long D_cap, uint32_t* __restrict__ tkeys,
             uint64_t* __restrict__ keys64, uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist0,
             uint32_t* __restrict__ counts, int mode, const uint32_t* __restrict__ flag_word) {
   __shared__ uint32_t s_warp[RS_WARPS];
   __shared__ uint32_t s_h0[256];     // digit-0 histogram of the emitted keys (first pass of the sort)
   __shared__ uint32_t s_bid, s_base;
-  if (threadIdx.x == 0) s_bid = (uint32_t)atomicAdd(const_cast<unsigned long long*>(chain), 1ull);
   s_h0[threadIdx.x] = 0;
+  // persistent CTAs (one wave): each takes tickets until the tiles of SC_TILE Gaussians are used up
+  while (true) {
+  __syncthreads();                   // s_bid / s_base of the previous round are no longer read
+  if (threadIdx.x == 0) s_bid = (uint32_t)atomicAdd(chain, 1ull);
   __syncthreads();
   const int bid = (int)s_bid;
+  if (bid >= num_blocks) break;
   // blocked arrangement: thread t owns SC_IPT consecutive Gaussians of the emission order
   const int first = bid * SC_TILE + threadIdx.x * SC_IPT;
-  uint32_t gid[SC_IPT], cnt[SC_IPT];
+  uint32_t gid[SC_IPT], cnt[SC_IPT], dk[SC_IPT];
+  ushort4 rc[SC_IPT];
   uint32_t mine = 0;
 #pragma unroll
   for (int k = 0; k < SC_IPT; ++k) {
@@ -381,33 +397,36 @@ emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ ord
     gid[k] = 0;
     if (j < P) gid[k] = order ? order[j] : (uint32_t)j;
   }
+  // one gather per Gaussian: the tile rectangle (all zero for a culled Gaussian) also gives the instance count
 #pragma unroll
   for (int k = 0; k < SC_IPT; ++k) {
-    cnt[k] = (first + k < P) ? tiles[gid[k]] : 0u;
+    rc[k] = (first + k < P) ? rect[gid[k]] : make_ushort4(0, 0, 0, 0);
+    dk[k] = (MODE == 1 && first + k < P) ? dkeys[gid[k]] : 0u;
+    cnt[k] = (uint32_t)(rc[k].z - rc[k].x) * (uint32_t)(rc[k].w - rc[k].y);
     mine += cnt[k];
   }
   uint32_t total;
   const uint32_t ex = block_exclusive_scan_256(mine, s_warp, &total);     // syncs inside
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    volatile unsigned long long* bst = chain + 2;
-    volatile unsigned long long* gst = bst + num_blocks;
+    unsigned long long* bst = chain + 2;
+    unsigned long long* gst = bst + num_blocks;
     const int j = bid % LB_GROUP, g = bid / LB_GROUP;
-    if (lane == 0) bst[bid] = CH_READY | (unsigned long long)total;
+    if (lane == 0) st_chain(bst + bid, CH_READY | (unsigned long long)total);
     unsigned long long sum = 0;
     if (lane < j) {
       unsigned long long v;
-      do { v = bst[bid - j + lane]; } while (!(v & CH_READY));
+      do { v = ld_chain(bst + (bid - j + lane)); } while (!(v & CH_READY));
       sum = v & ~CH_READY;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (j == LB_GROUP - 1 && lane == 0) gst[g] = CH_READY | (sum + total);
+    if (j == LB_GROUP - 1 && lane == 0) st_chain(gst + g, CH_READY | (sum + total));
     unsigned long long gsum = 0;
     for (int k0 = 0; k0 < g; k0 += 32) {
       if (k0 + lane < g) {
         unsigned long long v;
-        do { v = gst[k0 + lane]; } while (!(v & CH_READY));
+        do { v = ld_chain(gst + (k0 + lane)); } while (!(v & CH_READY));
         gsum += v & ~CH_READY;
       }
     }
@@ -444,11 +463,9 @@ emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ ord
 #pragma unroll
   for (int k = 0; k < SC_IPT; ++k) {
     if (cnt[k] == 0 || cnt[k] > BIG) continue;
-    const ushort4 rc = rect[gid[k]];
-    const uint32_t dk = (MODE == 1) ? dkeys[gid[k]] : 0u;
     long long o = offk[k];
-    for (int y = rc.y; y < rc.w; ++y)
-      for (int x = rc.x; x < rc.z; ++x) put(o++, (uint32_t)(y * gx + x), dk, gid[k]);
+    for (int y = rc[k].y; y < rc[k].w; ++y)
+      for (int x = rc[k].x; x < rc[k].z; ++x) put(o++, (uint32_t)(y * gx + x), dk[k], gid[k]);
   }
   // large splats (a Gaussian in front of a zoomed-in camera can touch every tile): one lane looping
   // over thousands of tiles would serialise the warp, so the 32 lanes share each of them
@@ -462,15 +479,16 @@ emit_kernel(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ ord
       const uint32_t g = __shfl_sync(0xffffffffu, gid[k], src);
       const uint32_t c = __shfl_sync(0xffffffffu, cnt[k], src);
       const uint32_t o0 = __shfl_sync(0xffffffffu, offk[k], src);
-      const ushort4 rc = rect[g];
-      const uint32_t dk = (MODE == 1) ? dkeys[g] : 0u;
-      const uint32_t wx = (uint32_t)(rc.z - rc.x);
+      const ushort4 rb = rect[g];
+      const uint32_t dkb = (MODE == 1) ? dkeys[g] : 0u;
+      const uint32_t wx = (uint32_t)(rb.z - rb.x);
       for (uint32_t i = lane; i < c; i += 32) {
-        const uint32_t y = rc.y + i / wx, x = rc.x + i % wx;
-        put((long long)o0 + i, y * (uint32_t)gx + x, dk, g);
+        const uint32_t y = rb.y + i / wx, x = rb.x + i % wx;
+        put((long long)o0 + i, y * (uint32_t)gx + x, dkb, g);
       }
     }
   }
+  }  // ticket loop
   __syncthreads();
   if (s_h0[threadIdx.x]) atomicAdd(&ghist0[threadIdx.x], s_h0[threadIdx.x]);
 }
@@ -642,7 +660,6 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   uint32_t* point_list = at<uint32_t>(saved, L.off_point_list);
   uint2* ranges = at<uint2>(saved, L.off_ranges);
   const ushort4* rect = at<ushort4>(scratch, L.off_rect);
-  const uint32_t* tiles = at<uint32_t>(scratch, L.off_tiles);
   const uint32_t* dkeys = at<uint32_t>(scratch, L.off_dkeys0);   // written by preprocess, kept intact
   unsigned long long* chain = at<unsigned long long>(scratch, L.off_blocksums);
   void* hist = at<char>(scratch, L.off_hist);
@@ -696,17 +713,26 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   uint64_t* kB64 = at<uint64_t>(scratch, L.off_keys64_1);
   uint32_t* tvA = inA ? point_list : alt_vals;
   uint32_t* tvB = inA ? alt_vals : point_list;
+  static std::atomic<int> sm_count{0};
+  int sms = sm_count.load(std::memory_order_relaxed);
+  if (sms == 0) {
+    int dev = 0;
+    GSB_CUDA(cudaGetDevice(&dev));
+    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sm_count.store(sms, std::memory_order_relaxed);
+  }
+  const int emit_grid = sc_blocks < sms * GSB_EMIT_MINB ? sc_blocks : sms * GSB_EMIT_MINB;
   GSB_CUDA(cudaMemsetAsync(chain, 0, emit_chain_words(sc_blocks) * sizeof(unsigned long long), st));
   // the prefiltered-violation flag of preprocess_fwd sits in the sort's counter row, which the next line zeroes
   // for the tile sort: park it in the spare chain word first
   GSB_CUDA(cudaMemcpyAsync(chain + 1, radix_flag_word(hist), sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   if ((rc = radix_prepare(D_cap, end_bit, hist, st))) return rc;
   if (two_level)
-    emit_kernel<0><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, order, P, chain, sc_blocks, rect, dkeys, v.gx, D_cap, tkB,
+    emit_kernel<0><<<emit_grid, RS_THREADS, 0, st>>>(order, P, chain, sc_blocks, rect, dkeys, v.gx, D_cap, tkB,
                                                      nullptr, tvB, radix_hist0(hist), counts, mode,
                                                      reinterpret_cast<const uint32_t*>(chain + 1));
   else
-    emit_kernel<1><<<sc_blocks, RS_THREADS, 0, st>>>(tiles, nullptr, P, chain, sc_blocks, rect, dkeys, v.gx, D_cap,
+    emit_kernel<1><<<emit_grid, RS_THREADS, 0, st>>>(nullptr, P, chain, sc_blocks, rect, dkeys, v.gx, D_cap,
                                                      nullptr, kB64, tvB, radix_hist0(hist), counts, mode,
                                                      reinterpret_cast<const uint32_t*>(chain + 1));
   GSB_POST_LAUNCH(debug, st, "emit_kernel");

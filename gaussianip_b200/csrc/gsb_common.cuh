@@ -166,9 +166,9 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
                     long long D_cap, int mode, uint32_t* host_counts, cudaEvent_t event, bool debug,
                     cudaStream_t st);
 
-int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
+int launch_render_fwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
-                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool transposed,
+                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, int variant,
                       bool debug, cudaStream_t st);
 
 int launch_render_bwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,

@@ -6,13 +6,15 @@
 // centres, radii and tile rectangles are bit-identical to the CPU oracle.  The kernel is
 // HBM-bound (reads 44+12K B, writes ~70 B per Gaussian), so giving up FMA contraction costs
 // nothing measurable.
+#include <atomic>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
 
 namespace {
 
-constexpr int PRE_IPT = 4;
+constexpr int PRE_CTAS_PER_SM = 4;   // 57 registers x 256 threads
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
@@ -81,6 +83,7 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
   if (!visible && v.prefiltered) *flag_word = 1u;
   int rad = 0;
   uint32_t ntiles = 0;
+  ushort4 rc = make_ushort4(0, 0, 0, 0);     // tile rectangle; stays empty for a culled Gaussian
   if (visible) {
     const float hx = ((sM[0] * px + sM[4] * py) + sM[8] * pz) + sM[12];
     const float hy = ((sM[1] * px + sM[5] * py) + sM[9] * pz) + sM[13];
@@ -197,12 +200,12 @@ preprocess_one(const View& v, int i, int K, const float* sV, const float* sM, co
         dst[1] = make_float4(cA * CONIC_SCALE_AC, cB * CONIC_SCALE_B, cC * CONIC_SCALE_AC, o);
         dst[2] = make_float4(tz, r_, g_, b_);
         clamped[i] = cl;
-        rect[i] = make_ushort4((unsigned short)minx, (unsigned short)miny, (unsigned short)maxx,
-                               (unsigned short)maxy);
+        rc = make_ushort4((unsigned short)minx, (unsigned short)miny, (unsigned short)maxx, (unsigned short)maxy);
       }
     }
   }
   radii[i] = visible ? rad : 0;
+  rect[i] = rc;                              // the emission kernel derives the instance count from it
   tiles[i] = visible ? ntiles : 0u;
   const uint32_t dk = visible ? __float_as_uint(tz) : 0xFFFFFFFFu;
   dkeys[i] = dk;
@@ -228,11 +231,13 @@ preprocess_fwd_kernel(View v, int P, int K, const float* __restrict__ means3D,
   if (threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   if (threadIdx.x == 32) load_intrinsics(v, sK);
   __syncthreads();
-  // PRE_IPT Gaussians per thread: 4x fewer CTAs flushing their 256-bin histogram to the same
-  // 256 global counters (one flush per 256 Gaussians cost +22 us of same-address L2 atomics)
+  // Persistent CTAs (one wave, 4 per SM) stride over the 256-Gaussian chunks: the grid of round 1 (4 chunks per
+  // CTA) was 1.65 waves at 1 M Gaussians, i.e. a third of the launch ran at partial occupancy (ncu r2:
+  // sm__cycles_active / elapsed 0.78).  Few CTAs also means few flushes of the 256-bin histogram to the same
+  // 256 global counters (one flush per 256 Gaussians cost +22 us of same-address L2 atomics).
 #pragma unroll 1
-  for (int k = 0; k < PRE_IPT; ++k) {
-    const int i = (blockIdx.x * PRE_IPT + k) * 256 + threadIdx.x;
+  for (int c = blockIdx.x; c * 256 < P; c += gridDim.x) {
+    const int i = c * 256 + threadIdx.x;
     if (i < P) preprocess_one(v, i, K, sV, sM, sCam, sK, means3D, scales, rots, opac, shs, colors, cov3Dp, radii, geom,
                               clamped, rect, tiles, dkeys, s_h0, flag_word);
   }
@@ -257,7 +262,16 @@ int launch_preprocess_fwd(const View& v, int P, int K, const float* means3D, con
                           uint8_t* clamped, ushort4* rect, uint32_t* tiles, uint32_t* dkeys,
                           void* radix_tmp, bool debug, cudaStream_t st) {
   if (P == 0) return GSB_OK;
-  const int grid = (P + 256 * PRE_IPT - 1) / (256 * PRE_IPT);
+  static std::atomic<int> sm_count{0};
+  int sms = sm_count.load(std::memory_order_relaxed);
+  if (sms == 0) {
+    int dev = 0;
+    GSB_CUDA(cudaGetDevice(&dev));
+    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sm_count.store(sms, std::memory_order_relaxed);
+  }
+  const int chunks = (P + 255) / 256;
+  const int grid = chunks < sms * PRE_CTAS_PER_SM ? chunks : sms * PRE_CTAS_PER_SM;
   // the kernel also accumulates the digit-0 histogram of the depth keys for the depth sort
   int rc = radix_prepare(P, 32, radix_tmp, st);
   if (rc) return rc;

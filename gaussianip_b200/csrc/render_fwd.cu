@@ -22,6 +22,10 @@
 // of the same records); one producer warp feeding a ring shared by the 8 consumers was slower too
 // (257-297 us: a single warp's gather latency cannot feed eight consumers).
 #include <atomic>
+#include <cstring>
+
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint)
+#include <cudaTypedefs.h>
 
 #include "gsb_common.cuh"
 
@@ -47,21 +51,59 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- TMA row gather (sm_100 cp.async.bulk.tensor ... tile::gather4) ------------------------------------------
+// G4 variant of the kernel below: Geom is described to the TMA unit as a 2-D fp32 tensor [P rows][12], box {16, 1}
+// (the 4 floats past a row are out of bounds and arrive as zeros, which gives the rows a 64-byte pitch in shared
+// memory: row k of a stage sits at k * 64, one multiply like the cp.async layout).  Eight lanes of a warp issue one
+// gather4 each (4 rows = 256 bytes, 128-byte aligned destination) instead of 3 x LDGSTS.128 on every lane;
+// completion is a per-(warp, stage) mbarrier with a transaction count.  scripts/micro/tma_gather4_probe.cu
+// measured the instruction in isolation (1.45-2x the LDGSTS row rate from L2).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* tm, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+constexpr int G4_ROW_FLOAT4 = 4;      // 64-byte row pitch of a gather4 stage
+constexpr size_t G4_STAGE_BYTES = 32 * G4_ROW_FLOAT4 * sizeof(float4);
+
 #ifndef GSB_FWD_MINB
 #define GSB_FWD_MINB 1
 #endif
-template <bool RECORD>
+template <bool RECORD, bool G4>
 __global__ void __launch_bounds__(WARPS * 32, GSB_FWD_MINB)
-render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
+render_fwd_kernel(View v, const __grid_constant__ CUtensorMap geom_map, const Geom* __restrict__ geom,
+                  const uint32_t* __restrict__ point_list,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                   float* __restrict__ out_color,
                   float* __restrict__ out_depth, float* __restrict__ out_alpha,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
                   uint2* __restrict__ hits, uint32_t* __restrict__ hit_count) {
-  extern __shared__ float4 smem_dyn[];             // 12 KB per stage per CTA
+  extern __shared__ __align__(128) float4 smem_dyn[];   // cp.async: 12 KB per stage per CTA; gather4: 16 KB
   float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
+  constexpr size_t RING_FLOAT4 = G4 ? (size_t)WARPS * STAGES * 32 * G4_ROW_FLOAT4 : (size_t)WARPS * STAGES * 3 * 32;
   // RECORD: per warp and half, the blend masks of the current chunk's 32 instances
-  uint32_t (*s_mask)[2][32] = reinterpret_cast<uint32_t (*)[2][32]>(smem_dyn + WARPS * STAGES * 3 * 32);
+  uint32_t (*s_mask)[2][32] = reinterpret_cast<uint32_t (*)[2][32]>(smem_dyn + RING_FLOAT4);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_dyn + RING_FLOAT4 + WARPS * 2 * 32 / 4);   // [WARPS][STAGES] (G4)
 
   const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
   const int tx = tile % v.gx, ty = tile / v.gx;
@@ -98,7 +140,33 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
 
   if (chunks > 0 && __any_sync(0xffffffffu, T != 0.0f)) {
     float4 (*ring)[3][32] = s_rec[warp];
+    float4* ring4 = smem_dyn + (size_t)warp * STAGES * 32 * G4_ROW_FLOAT4;      // G4: [STAGES][32 rows][4 float4]
+    uint64_t* bars = s_bar + warp * STAGES;
+    if (G4) {
+      if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncwarp();
+    }
+    int in_flight = -1;                            // G4: last chunk handed to the TMA unit
     auto issue = [&](int c, uint32_t gid) {      // stage chunk c (lane's instance) into the ring
+      if (G4) {
+        if (c < chunks) {                          // warp-uniform; lanes past the end of the list fetch row 0
+          const int id1 = (int)__shfl_down_sync(0xffffffffu, gid, 1), id2 = (int)__shfl_down_sync(0xffffffffu, gid, 2),
+                    id3 = (int)__shfl_down_sync(0xffffffffu, gid, 3);
+          if (lane == 0) mbar_expect_tx(&bars[c & (STAGES - 1)], (uint32_t)G4_STAGE_BYTES);
+          if ((lane & 3) == 0) {
+            // the slot was read with ordinary loads until the __syncwarp that ended the previous round
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_gather4(ring4 + ((size_t)(c & (STAGES - 1)) * 32 + lane) * G4_ROW_FLOAT4, &geom_map, (int)gid, id1, id2,
+                        id3, &bars[c & (STAGES - 1)]);
+          }
+          in_flight = c;
+        }
+        return;
+      }
       if (c < chunks) {
         if (c * 32 + lane < n) {
           const float4* src = reinterpret_cast<const float4*>(geom + gid);
@@ -126,9 +194,18 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       issue(c + STAGES - 1, gid_next);
       gid_next = fetch_gid(c + STAGES);
       if (RECORD) { s_mask[warp][0][lane] = 0u; s_mask[warp][1][lane] = 0u; }
-      cp_async_wait<STAGES - 1>();               // chunk c has landed (for this lane)
+      if (G4) {
+        mbar_wait(&bars[c & (STAGES - 1)], (uint32_t)((c / STAGES) & 1));     // chunk c has landed
+      } else {
+        cp_async_wait<STAGES - 1>();             // chunk c has landed (for this lane)
+      }
       __syncwarp();                              // ... and for every lane of the warp
       float4 (*st)[32] = ring[c & (STAGES - 1)];
+      const float4* st4 = ring4 + (size_t)(c & (STAGES - 1)) * 32 * G4_ROW_FLOAT4;
+      // record r of the stage: three float4 (cp.async: three planes of 32; gather4: one 64-byte row)
+      auto rec0 = [&](int r) -> float4 { return G4 ? st4[r * G4_ROW_FLOAT4] : st[0][r]; };
+      auto rec1 = [&](int r) -> float4 { return G4 ? st4[r * G4_ROW_FLOAT4 + 1] : st[1][r]; };
+      auto rec2 = [&](int r) -> float4 { return G4 ? st4[r * G4_ROW_FLOAT4 + 2] : st[2][r]; };
       const int e = c * 32 + lane;
       const bool done = T == 0.0f;
       const uint32_t alive = __ballot_sync(0xffffffffu, !done);
@@ -153,7 +230,7 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
       }
       bool hitA = false, hitB = false;
       if (e < n) {
-        const float4 a = st[0][lane];
+        const float4 a = rec0(lane);
         hitA = (fabsf(a.x - cxA) <= a.z + hwxA) && (fabsf(a.y - cyA) <= a.w + hwyA);
         hitB = (fabsf(a.x - cxB) <= a.z + hwxB) && (fabsf(a.y - cyB) <= a.w + hwyB);
       }
@@ -180,9 +257,9 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
         for (int i = 0; i < HB; ++i) {
           al[i] = 0.0f;
           if (k[i] >= 0) {
-            const float4 a = st[0][k[i]];     // x, y, -, -
-            const float4 q = st[1][k[i]];     // pre-scaled conic (qa, qb, qc), opacity
-            ff[i] = st[2][k[i]];              // depth, r, g, b
+            const float4 a = rec0(k[i]);      // x, y, -, -
+            const float4 q = rec1(k[i]);      // pre-scaled conic (qa, qb, qc), opacity
+            ff[i] = rec2(k[i]);               // depth, r, g, b
             const float dx = a.x - pxf, dy = a.y - pyf;
             const float e2 = gauss_exponent2(q.x, q.y, q.z, dx, dy);      // log2 of the Gaussian weight
             al[i] = e2 <= 0.0f ? fminf(ALPHA_CAP, q.w * exp2_blend(e2)) : 0.0f;
@@ -219,10 +296,15 @@ render_fwd_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restr
         rec_n += __popc(nz);
         gid_cur = gid_issued;
       }
-      if (__all_sync(0xffffffffu, T == 0.0f)) break;
+      if (__all_sync(0xffffffffu, T == 0.0f)) {
+        // a warp that stops early still owns the chunk in flight: the TMA unit must not write into shared memory
+        // of a CTA that has exited
+        if (G4 && in_flight > c) mbar_wait(&bars[in_flight & (STAGES - 1)], (uint32_t)((in_flight / STAGES) & 1));
+        break;
+      }
       __syncwarp();                              // ring slot c is free before it is refilled
     }
-    cp_async_wait<0>();
+    if (!G4) cp_async_wait<0>();
   }
   if (RECORD && lane == 0) hit_count[tile * WARPS + warp] = (uint32_t)rec_n;
 
@@ -488,22 +570,51 @@ render_fwd_transposed_kernel(View v, const Geom* __restrict__ geom, const uint32
 
 }  // namespace
 
-int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_list,
+// Tensor map of the Geom array for the gather4 variant: fp32 [P rows][12], box {16, 1}, no swizzle.
+static int make_geom_map(const Geom* geom, int P, CUtensorMap* tm) {
+  static std::atomic<PFN_cuTensorMapEncodeTiled_v12000> encode{nullptr};
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode.load(std::memory_order_acquire);
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* sym = nullptr;
+    GSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    if (!sym) return GSB_E_UNSUPPORTED;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+    encode.store(fn, std::memory_order_release);
+  }
+  const cuuint64_t gdim[2] = {12, (cuuint64_t)(P > 0 ? P : 1)};
+  const cuuint64_t gstr[1] = {sizeof(Geom)};
+  const cuuint32_t box[2] = {16, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<Geom*>(geom), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GSB_OK : GSB_E_CUDA;
+}
+
+// variant: 0 per-hit blend with cp.async gathers (default), 1 transposed two-phase blend, 2 per-hit blend with TMA
+// gather4 row gathers
+int launch_render_fwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
-                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, bool transposed,
+                      uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, int variant,
                       bool debug, cudaStream_t st) {
   const int T = v.gx * v.gy;
   if (T == 0) return GSB_OK;
+  const bool transposed = variant == 1;
 #ifndef GSB_FWD_SMEM_PAD
 #define GSB_FWD_SMEM_PAD 0
 #endif
   constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4) + (size_t)WARPS * 2 * 32 * sizeof(uint32_t) + GSB_FWD_SMEM_PAD;
+  constexpr size_t smem_g4 = (size_t)WARPS * STAGES * G4_STAGE_BYTES + (size_t)WARPS * 2 * 32 * sizeof(uint32_t) +
+                             (size_t)WARPS * STAGES * sizeof(uint64_t) + GSB_FWD_SMEM_PAD;
   static std::atomic<unsigned long long> configured{0};   // bit per device: the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
   if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
-    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g4));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g4));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_transposed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(WARPS * F2_WARP_BYTES + GSB_FWD_SMEM_PAD)));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_transposed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -521,12 +632,26 @@ int launch_render_fwd(const View& v, const Geom* geom, const uint32_t* point_lis
     GSB_POST_LAUNCH(debug, st, "render_fwd_transposed_kernel");
     return GSB_OK;
   }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (variant == 2) {
+    const int rc = make_geom_map(geom, P, &tm);
+    if (rc) return rc;
+    if (hits && hit_count)
+      render_fwd_kernel<true, true><<<T, WARPS * 32, smem_g4, st>>>(v, tm, geom, point_list, ranges, tile_order, color,
+                                                                    depth, alpha, n_contrib, final_T, hits, hit_count);
+    else
+      render_fwd_kernel<false, true><<<T, WARPS * 32, smem_g4, st>>>(v, tm, geom, point_list, ranges, tile_order, color,
+                                                                     depth, alpha, n_contrib, final_T, nullptr, nullptr);
+    GSB_POST_LAUNCH(debug, st, "render_fwd_kernel<gather4>");
+    return GSB_OK;
+  }
   if (hits && hit_count)
-    render_fwd_kernel<true><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth,
-                                                         alpha, n_contrib, final_T, hits, hit_count);
+    render_fwd_kernel<true, false><<<T, WARPS * 32, smem, st>>>(v, tm, geom, point_list, ranges, tile_order, color,
+                                                                depth, alpha, n_contrib, final_T, hits, hit_count);
   else
-    render_fwd_kernel<false><<<T, WARPS * 32, smem, st>>>(v, geom, point_list, ranges, tile_order, color, depth,
-                                                          alpha, n_contrib, final_T, nullptr, nullptr);
+    render_fwd_kernel<false, false><<<T, WARPS * 32, smem, st>>>(v, tm, geom, point_list, ranges, tile_order, color,
+                                                                 depth, alpha, n_contrib, final_T, nullptr, nullptr);
   GSB_POST_LAUNCH(debug, st, "render_fwd_kernel");
   return GSB_OK;
 }

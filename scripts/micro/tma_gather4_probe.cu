@@ -24,15 +24,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+  // bounded spin: a transaction count that never completes (wrong expect_tx) traps instead of hanging the GPU
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) asm volatile("trap;");
+  }
 }
 __device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* tm, int col, int r0, int r1, int r2, int r3,
                                             uint64_t* bar) {
@@ -47,7 +50,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 
 // Every warp gathers `chunks` x 32 rows (ids from `idx`) into its own stage and accumulates a checksum; with
 // chunks == 1 the rows themselves are written out for the correctness check.
-template <bool TMA>
+template <bool TMA, int PITCH>
 __global__ void __launch_bounds__(WARPS * 32)
 gather_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ table, const uint32_t* __restrict__ idx,
               int chunks, float* __restrict__ rows_out, float* __restrict__ sums) {
@@ -69,12 +72,12 @@ gather_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ 
     if (TMA) {
       const int id1 = __shfl_down_sync(0xffffffffu, id, 1), id2 = __shfl_down_sync(0xffffffffu, id, 2),
                 id3 = __shfl_down_sync(0xffffffffu, id, 3);
-      if (lane == 0) mbar_expect_tx(&bars[warp][c & 1], 32 * ROW_FLOATS * 4);
+      if (lane == 0) mbar_expect_tx(&bars[warp][c & 1], 32 * PITCH * 4);
       __syncwarp();
       if ((lane & 3) == 0) tma_gather4(dst + (lane >> 2) * 64, &tm, 0, (int)id, id1, id2, id3, &bars[warp][c & 1]);
     } else {
       const float4* src = reinterpret_cast<const float4*>(table + (size_t)id * ROW_FLOATS);
-      float4* d4 = reinterpret_cast<float4*>(dst + (lane >> 2) * 64 + (lane & 3) * ROW_FLOATS);
+      float4* d4 = reinterpret_cast<float4*>(dst + (lane >> 2) * 64 + (lane & 3) * PITCH);
       cp_async16(d4, src); cp_async16(d4 + 1, src + 1); cp_async16(d4 + 2, src + 2);
       asm volatile("cp.async.commit_group;\n" ::);
     }
@@ -89,12 +92,12 @@ gather_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ 
     const float* st = stage[warp][c & 1];
     // consume like the blend kernels: broadcast reads of every row's first float4
     for (int k = 0; k < 32; k += 4) {
-      const float4 a = *reinterpret_cast<const float4*>(st + (k >> 2) * 64 + (k & 3) * ROW_FLOATS);
+      const float4 a = *reinterpret_cast<const float4*>(st + (k >> 2) * 64 + (k & 3) * PITCH);
       acc += a.x + a.y * 0.5f + a.z * 0.25f + a.w;
     }
     if (chunks == 1 && rows_out)
       for (int j = 0; j < ROW_FLOATS; ++j)
-        rows_out[(((size_t)blockIdx.x * WARPS + warp) * 32 + lane) * ROW_FLOATS + j] = st[(lane >> 2) * 64 + (lane & 3) * ROW_FLOATS + j];
+        rows_out[(((size_t)blockIdx.x * WARPS + warp) * 32 + lane) * ROW_FLOATS + j] = st[(lane >> 2) * 64 + (lane & 3) * PITCH + j];
     __syncwarp();
   }
   if (!TMA) asm volatile("cp.async.wait_group 0;\n" ::);
@@ -118,19 +121,21 @@ int main() {
   uint32_t* d_idx; CK(cudaMalloc(&d_idx, n_idx * 4)); CK(cudaMemcpy(d_idx, hidx.data(), n_idx * 4, cudaMemcpyHostToDevice));
   float *d_rows, *d_sums;
   CK(cudaMalloc(&d_rows, (size_t)grid * WARPS * 32 * ROW_FLOATS * 4)); CK(cudaMalloc(&d_sums, (size_t)grid * WARPS * 4));
-  for (int boxh : {1, 4}) {
+  for (int boxw : {12, 16}) {
+    const int boxh = 1;
     CUtensorMap tm;
     cuuint64_t gdim[2] = {ROW_FLOATS, (cuuint64_t)P};
     cuuint64_t gstr[1] = {ROW_FLOATS * 4};
-    cuuint32_t box[2] = {ROW_FLOATS, (cuuint32_t)boxh};
+    cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)boxh};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_table, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    printf("box {12,%d}: encode -> %d\n", boxh, (int)r);
+    printf("box {%d,%d} on 12-float rows: encode -> %d\n", boxw, boxh, (int)r);
     if (r != CUDA_SUCCESS) continue;
     // correctness: one chunk per warp
     CK(cudaMemset(d_rows, 0, (size_t)grid * WARPS * 32 * ROW_FLOATS * 4));
-    gather_kernel<true><<<grid, WARPS * 32>>>(tm, d_table, d_idx, 1, d_rows, d_sums);
+    if (boxw == 12) gather_kernel<true, 12><<<grid, WARPS * 32>>>(tm, d_table, d_idx, 1, d_rows, d_sums);
+    else gather_kernel<true, 16><<<grid, WARPS * 32>>>(tm, d_table, d_idx, 1, d_rows, d_sums);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("  gather4 kernel failed: %s\n", cudaGetErrorString(e)); return 2; }
     std::vector<float> rows((size_t)grid * WARPS * 32 * ROW_FLOATS);
@@ -146,11 +151,15 @@ int main() {
     for (int rep = 0; rep < 2; ++rep) {
       cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
       float ms_t = 0.f, ms_l = 0.f;
-      gather_kernel<true><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums);
-      CK(cudaEventRecord(a)); gather_kernel<true><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums); CK(cudaEventRecord(b));
+      auto run_t = [&]() {
+        if (boxw == 12) gather_kernel<true, 12><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums);
+        else gather_kernel<true, 16><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums);
+      };
+      run_t();
+      CK(cudaEventRecord(a)); run_t(); CK(cudaEventRecord(b));
       CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms_t, a, b));
-      gather_kernel<false><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums);
-      CK(cudaEventRecord(a)); gather_kernel<false><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums); CK(cudaEventRecord(b));
+      gather_kernel<false, 12><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums);
+      CK(cudaEventRecord(a)); gather_kernel<false, 12><<<grid, WARPS * 32>>>(tm, d_table, d_idx, chunks_timed, nullptr, d_sums); CK(cudaEventRecord(b));
       CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms_l, a, b));
       const double rows_total = (double)grid * WARPS * chunks_timed * 32;
       printf("  %.0f M rows of 48 B: gather4 %.3f ms (%.1f G rows/s), LDGSTS %.3f ms (%.1f G rows/s)\n", rows_total * 1e-6, ms_t,
