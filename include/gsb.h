@@ -294,7 +294,10 @@ int gsb_gather_rows(int n_tensors, const float* const* src, float* const* dst, c
  *      butterfly (cross-check of 0);
  *   3  native forward + the record-free backward that re-walks the tile lists with per-warp culling (the
  *      round-1 kernel; cross-check of 0);
- *   4  as 3 with a packed shared-memory reduction. */
+ *   4  as 3 with a packed shared-memory reduction;
+ *   10 / 11 / 12  select the FORWARD blend only (backward choice unchanged): 10 per-hit blend staged with cp.async
+ *      (default), 11 transposed two-phase blend, 12 per-hit blend staged with the sm_100 TMA row gather
+ *      (cp.async.bulk.tensor ... tile::gather4; measured alternatives, all parity-green). */
 int gsb_set_blend_variant(int variant);
 
 /* Test / measurement helpers. */
