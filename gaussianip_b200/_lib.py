@@ -104,7 +104,7 @@ def load() -> C.CDLL:
     # A/B switch for measurements and for running the whole parity suite on the other forward blend kernel
     fv = os.environ.get("GSB_FWD_VARIANT")
     if fv:
-        lib.gsb_set_blend_variant({"per_hit": 10, "transposed": 11, "gather4": 12}[fv])
+        lib.gsb_set_blend_variant({"per_hit": 10, "transposed": 11, "gather4": 12, "precull": 13}[fv])
     _lib = lib
     return lib
 

@@ -184,7 +184,7 @@ int gsb_adam_step(int n_groups, float* const* params, const float* const* grads,
 int gsb_set_blend_variant(int variant) {
   // 10 / 11 / 12 select the forward blend kernel (per-hit with cp.async gathers / transposed / per-hit with TMA
   // gather4 row gathers) and leave the backward choice alone
-  if (variant >= 10 && variant <= 12) { g_fwd_variant.store(variant - 10); return GSB_OK; }
+  if (variant >= 10 && variant <= 13) { g_fwd_variant.store(variant - 10); return GSB_OK; }
   if (variant < 0 || variant > 4) return GSB_E_INVALID;
   g_blend_variant.store(variant);
   return GSB_OK;

@@ -323,6 +323,268 @@ render_fwd_kernel(View v, const __grid_constant__ CUtensorMap geom_map, const Ge
 }
 
 
+// ---- forward blend with a CTA-wide pre-cull --------------------------------------------------------------------
+// In the kernel above every one of a tile's 8 warps walks the WHOLE tile list: it gathers the 48-byte record of every
+// instance and tests it against its own 8x4 pixels, although only ~19 % of the instances reach a given warp (ncu:
+// ~110 warp instructions per 32-instance chunk and warp, 27 % of the kernel; every record is fetched 8 times per CTA).
+// Here the CTA first classifies the list ONCE (phase 0: the 8 warps share the chunks; lane = instance loads only the
+// first 16 bytes of the record and writes an 8-bit mask of the warp regions the splat's conservative extent box
+// overlaps — the same test as below with the static 8x4 rectangles, so nothing that could blend is dropped).  After
+// one __syncthreads each warp scans the byte masks (a load, a ballot and a count per 32 instances), queues the
+// positions of ITS instances and gathers / tests / blends dense chunks of 32 of them exactly like the kernel above
+// (same per-half dynamic rectangles, same arithmetic, same list order, so images, contributor counts and hit records
+// are identical).  MEASURED (r2v / r2w, profiles/r2_experiments.md): 139.5 M warp instructions per launch instead of
+// 149.2 M, but IPC 2.5 instead of 2.7 (the scan's id load sits on the warp's critical path): 224.5 us against 223.2 us
+// per view — no gain, so the kernel above stays the default.  Staging the ids in shared memory as well (+32 KB per
+// CTA, taken from L1) and four 4x2 hit streams per warp instead of two 4x4 ones were both slower (249 / 251 us).
+constexpr int PC_CAP = 8192;           // instances of a tile that get a mask byte; the rest of a longer list is taken by every warp
+constexpr int PC_QUEUE = 64;           // queued (Gaussian id, list position) pairs per warp (power of two, >= 63)
+#ifndef GSB_PC_UNITS
+#define GSB_PC_UNITS 2
+#endif
+// UNITS = hit streams per warp: 2 = the two 4x4 halves (as above), 4 = four 4x2 quarters (lanes 8u .. 8u+7), each
+// taking its own hits from a chunk: fewer iterations when a splat reaches only part of a half.
+constexpr int PC_UNITS = GSB_PC_UNITS;
+static_assert(PC_UNITS == 2 || PC_UNITS == 4, "halves or quarters");
+constexpr size_t PC_SMEM_BYTES = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4) + (size_t)WARPS * PC_UNITS * 32 * sizeof(uint32_t) +
+                                 (size_t)WARPS * PC_QUEUE * sizeof(uint2) + PC_CAP;
+
+template <bool RECORD>
+__global__ void __launch_bounds__(WARPS * 32, GSB_FWD_MINB)
+render_fwd_precull_kernel(View v, const Geom* __restrict__ geom, const uint32_t* __restrict__ point_list,
+                          const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                          float* __restrict__ out_color, float* __restrict__ out_depth,
+                          float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
+                          float* __restrict__ final_T, uint2* __restrict__ hits, uint32_t* __restrict__ hit_count) {
+  constexpr int U = PC_UNITS, LU = 32 / U;          // lanes per unit
+  extern __shared__ __align__(128) float4 smem_dyn[];
+  float4 (*s_rec)[STAGES][3][32] = reinterpret_cast<float4 (*)[STAGES][3][32]>(smem_dyn);
+  uint32_t (*s_mask)[U][32] = reinterpret_cast<uint32_t (*)[U][32]>(smem_dyn + WARPS * STAGES * 3 * 32);
+  uint2 (*s_q)[PC_QUEUE] = reinterpret_cast<uint2 (*)[PC_QUEUE]>(s_mask + WARPS);
+  uint8_t* s_wm = reinterpret_cast<uint8_t*>(s_q + WARPS);
+
+  const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles are launched first
+  const int tx = tile % v.gx, ty = tile / v.gx;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int unit = lane / LU;
+  const uint32_t unit_lanes = (U == 4 ? 0xffu : 0xffffu) << (unit * LU);
+  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  const int lx = lane_px(lane), ly = lane_py(lane);
+  const int pix_x = tx * TILE_X + wx + lx;
+  const int pix_y = ty * TILE_Y + wy + ly;
+  const bool inside = pix_x < v.W && pix_y < v.H;
+  const float pxf = (float)pix_x, pyf = (float)pix_y;
+  // Cull rectangles, one per unit = bounding box of the unit's pixels that are still accumulating (pixel centres).
+  // Unit u of 2: x0 = 4u, y0 = 0, 4x4.  Unit u of 4 (lanes 8u..8u+7): x0 = 4 (u >> 1), y0 = 2 (u & 1), 4x2.
+  const float bx = (float)(tx * TILE_X + wx), by = (float)(ty * TILE_Y + wy);
+  float cx[U], cy[U], hwx[U], hwy[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int x0 = U == 4 ? 4 * (u >> 1) : 4 * u, y0 = U == 4 ? 2 * (u & 1) : 0;
+    hwx[u] = 1.5f; hwy[u] = U == 4 ? 0.5f : 1.5f;
+    cx[u] = bx + (float)x0 + hwx[u]; cy[u] = by + (float)y0 + hwy[u];
+  }
+  uint32_t alive_prev = 0xffffffffu;
+
+  const uint2 range = ranges[tile];
+  const int n = (int)(range.y - range.x);
+  const uint32_t* pl = point_list + range.x;
+
+  // ---- phase 0: which warp regions can each instance reach (once per CTA) ----
+  {
+    const int n_m = n < PC_CAP ? n : PC_CAP;
+    const float tx0 = (float)(tx * TILE_X), ty0 = (float)(ty * TILE_Y);
+#pragma unroll 2
+    for (int e = warp * 32 + lane; e < n_m; e += WARPS * 32) {
+      const uint32_t gid = pl[e];
+      const float4 a = *reinterpret_cast<const float4*>(geom + gid);      // x, y, extent x, extent y
+      // warp region (c, r): pixel centres x in [tx0 + 8c, +7], y in [ty0 + 4r, +3]
+      const float ex = a.z + 3.5f, ey = a.w + 1.5f;
+      const uint32_t c0 = fabsf(a.x - (tx0 + 3.5f)) <= ex, c1 = fabsf(a.x - (tx0 + 11.5f)) <= ex;
+      const uint32_t cm = c0 | (c1 << 1);                                    // warps 0/1 of a row
+      uint32_t m = 0u;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (fabsf(a.y - (ty0 + 1.5f + 4.0f * (float)r)) <= ey) m |= cm << (2 * r);
+      s_wm[e] = (uint8_t)m;
+    }
+  }
+  __syncthreads();
+
+  float T = inside ? 1.0f : 0.0f, T_live = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f, A = 0.f;
+  uint32_t last = 0;
+  uint2* rec_base = RECORD ? hits + ((size_t)range.x * WARPS + (size_t)warp * (size_t)n) : nullptr;
+  int rec_n = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+
+  if (n > 0 && __any_sync(0xffffffffu, T != 0.0f)) {
+    float4 (*ring)[3][32] = s_rec[warp];
+    uint2* q = s_q[warp];
+    int scan = 0, q_head = 0, q_cnt = 0;
+    // queue this warp's instances of whole 32-instance chunks until a dense chunk is available
+    auto scan_more = [&]() {
+      while (q_cnt < 32 && scan < n) {
+        const int e = scan + lane;
+        uint32_t m = 0u;
+        if (e < n) m = e < PC_CAP ? (uint32_t)s_wm[e] : 0xffu;
+        const bool mine = (m >> warp) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+        if (bal) {
+          if (mine) q[(q_head + q_cnt + __popc(bal & lt)) & (PC_QUEUE - 1)] = make_uint2(pl[e], (uint32_t)e);
+          q_cnt += __popc(bal);
+        }
+        scan += 32;
+      }
+      __syncwarp();
+    };
+    // take up to 32 queued instances: returns how many; lane l < count receives entry l
+    auto pop = [&](uint2& ent) -> int {
+      const int cnt = q_cnt < 32 ? q_cnt : 32;
+      ent = make_uint2(0u, 0u);
+      if (lane < cnt) ent = q[(q_head + lane) & (PC_QUEUE - 1)];
+      q_head = (q_head + cnt) & (PC_QUEUE - 1);
+      q_cnt -= cnt;
+      __syncwarp();                               // the entries are read before scan_more overwrites the slots
+      return cnt;
+    };
+    auto issue = [&](int slot, int cnt, uint32_t gid) {      // stage a dense chunk (lane's instance) into the ring
+      if (lane < cnt) {
+        const float4* src = reinterpret_cast<const float4*>(geom + gid);
+        float4 (*st)[32] = ring[slot];
+        cp_async16(&st[0][lane], src);
+        cp_async16(&st[1][lane], src + 1);
+        cp_async16(&st[2][lane], src + 2);
+      }
+      cp_async_commit();                         // always commit: keeps the group count uniform
+    };
+    static_assert(STAGES == 2, "one dense chunk in flight while one is blended");
+    uint2 cur, nxt;
+    scan_more();
+    int cnt_cur = pop(cur);
+    issue(0, cnt_cur, cur.x);
+    for (int c = 0; cnt_cur > 0; ++c) {
+      scan_more();
+      const int cnt_nxt = pop(nxt);
+      issue((c + 1) & 1, cnt_nxt, nxt.x);
+      if (RECORD) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) s_mask[warp][u][lane] = 0u;
+      }
+      cp_async_wait<1>();                        // dense chunk c has landed (for this lane)
+      __syncwarp();                              // ... and for every lane of the warp
+      float4 (*st)[32] = ring[c & 1];
+      const bool done = T == 0.0f;
+      const uint32_t alive = __ballot_sync(0xffffffffu, !done);
+      if (alive != alive_prev) {
+        const uint32_t changed = alive ^ alive_prev;
+        alive_prev = alive;
+        const int hx = lane & 3;                             // x inside the unit
+        const int hy = U == 4 ? ((lane >> 2) & 1) : ly;      // y inside the unit
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t um = (U == 4 ? 0xffu : 0xffffu) << (u * LU);
+          if (changed & um) {                                // warp-uniform
+            const bool on = !done && unit == u;
+            const int x0 = __reduce_min_sync(0xffffffffu, on ? hx : 64), x1 = __reduce_max_sync(0xffffffffu, on ? hx : -1);
+            const int y0 = __reduce_min_sync(0xffffffffu, on ? hy : 64), y1 = __reduce_max_sync(0xffffffffu, on ? hy : -1);
+            const int ux = U == 4 ? 4 * (u >> 1) : 4 * u, uy = U == 4 ? 2 * (u & 1) : 0;
+            hwx[u] = 0.5f * (float)(x1 - x0); hwy[u] = 0.5f * (float)(y1 - y0);
+            cx[u] = bx + (float)(ux + x0) + hwx[u]; cy[u] = by + (float)(uy + y0) + hwy[u];
+          }
+        }
+      }
+      // every lane keeps the pending hits of ITS unit (a unit without live pixels takes none: its rectangle is
+      // empty, but negative half-widths can still pass the test for degenerate splats of infinite extent)
+      uint32_t pend = 0u;
+      {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool have = lane < cnt_cur;
+        if (have) a = st[0][lane];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool h = have && (fabsf(a.x - cx[u]) <= a.z + hwx[u]) && (fabsf(a.y - cy[u]) <= a.w + hwy[u]);
+          const uint32_t mk = __ballot_sync(0xffffffffu, h);
+          if (unit == u) pend = mk;
+        }
+      }
+      if (!(alive & unit_lanes)) pend = 0u;
+      while (__any_sync(0xffffffffu, pend != 0u)) {
+        int k[HB];
+        uint32_t posk[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          k[i] = __ffs(pend) - 1;               // -1 when this unit has no hit left
+          pend &= pend - 1;
+          posk[i] = __shfl_sync(0xffffffffu, cur.y, k[i] & 31);   // list position of that instance
+        }
+        float al[HB];
+        float4 ff[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          al[i] = 0.0f;
+          if (k[i] >= 0) {
+            const float4 a = st[0][k[i]];     // x, y, -, -
+            const float4 qq = st[1][k[i]];    // pre-scaled conic (qa, qb, qc), opacity
+            ff[i] = st[2][k[i]];              // depth, r, g, b
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float e2 = gauss_exponent2(qq.x, qq.y, qq.z, dx, dy);      // log2 of the Gaussian weight
+            al[i] = e2 <= 0.0f ? fminf(ALPHA_CAP, qq.w * exp2_blend(e2)) : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          bool ok = false;
+          if (k[i] >= 0 && al[i] >= ALPHA_MIN) {
+            const float test_T = T * (1.0f - al[i]);
+            ok = test_T >= T_MIN;
+            if (ok) {
+              const float w = al[i] * T;
+              C0 += ff[i].y * w; C1 += ff[i].z * w; C2 += ff[i].w * w;
+              Dz += ff[i].x * w; A += w;
+              T_live = test_T;
+              last = posk[i] + 1u;
+            }
+            T = ok ? test_T : 0.0f;       // a saturating splat (or a finished pixel) leaves T at 0
+          }
+          if (RECORD) {
+            // the unit's bits of the vote: the pixels of this unit that blended its Gaussian
+            const uint32_t vb = __ballot_sync(0xffffffffu, ok);
+            if ((lane & (LU - 1)) == 0 && k[i] >= 0) s_mask[warp][unit][k[i]] = vb & unit_lanes;
+          }
+        }
+      }
+      if (RECORD) {
+        __syncwarp();
+        uint32_t m = 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) m |= s_mask[warp][u][lane];
+        const uint32_t nz = __ballot_sync(0xffffffffu, m != 0u);
+        if (m) rec_base[rec_n + __popc(nz & lt)] = make_uint2(cur.x, m);
+        rec_n += __popc(nz);
+      }
+      if (__all_sync(0xffffffffu, T == 0.0f)) break;
+      __syncwarp();                              // ring slot c is free before it is refilled
+      cur = nxt;
+      cnt_cur = cnt_nxt;
+    }
+    cp_async_wait<0>();
+  }
+  if (RECORD && lane == 0) hit_count[tile * WARPS + warp] = (uint32_t)rec_n;
+
+  if (inside) {
+    T = T_live;
+    const size_t hw = (size_t)v.H * v.W;
+    const size_t pix = (size_t)pix_y * v.W + pix_x;
+    out_color[pix] = C0 + T * v.bg[0];
+    out_color[hw + pix] = C1 + T * v.bg[1];
+    out_color[2 * hw + pix] = C2 + T * v.bg[2];
+    out_depth[pix] = Dz;
+    out_alpha[pix] = A;
+    n_contrib[pix] = last;
+    final_T[pix] = T;
+  }
+}
+
 // ---- transposed forward blend ------------------------------------------------------------------------------------
 // The kernel above evaluates one (half, Gaussian) hit per iteration with ~9 of 32 lanes on a pixel the splat reaches.
 // This one collects the hits of successive chunks into blocks of 32 and handles a block in two phases with
@@ -593,7 +855,7 @@ static int make_geom_map(const Geom* geom, int P, CUtensorMap* tm) {
 }
 
 // variant: 0 per-hit blend with cp.async gathers (default), 1 transposed two-phase blend, 2 per-hit blend with TMA
-// gather4 row gathers
+// gather4 row gathers, 3 per-hit blend behind a CTA-wide pre-cull
 int launch_render_fwd(const View& v, int P, const Geom* geom, const uint32_t* point_list,
                       const uint2* ranges, const uint32_t* tile_order, float* color, float* depth, float* alpha,
                       uint32_t* n_contrib, float* final_T, uint2* hits, uint32_t* hit_count, int variant,
@@ -607,6 +869,7 @@ int launch_render_fwd(const View& v, int P, const Geom* geom, const uint32_t* po
   constexpr size_t smem = (size_t)WARPS * STAGES * 3 * 32 * sizeof(float4) + (size_t)WARPS * 2 * 32 * sizeof(uint32_t) + GSB_FWD_SMEM_PAD;
   constexpr size_t smem_g4 = (size_t)WARPS * STAGES * G4_STAGE_BYTES + (size_t)WARPS * 2 * 32 * sizeof(uint32_t) +
                              (size_t)WARPS * STAGES * sizeof(uint64_t) + GSB_FWD_SMEM_PAD;
+  constexpr size_t smem_pc = PC_SMEM_BYTES + GSB_FWD_SMEM_PAD;
   static std::atomic<unsigned long long> configured{0};   // bit per device: the attribute is per device
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
@@ -615,6 +878,8 @@ int launch_render_fwd(const View& v, int P, const Geom* geom, const uint32_t* po
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g4));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g4));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_precull_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pc));
+    GSB_CUDA(cudaFuncSetAttribute(render_fwd_precull_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pc));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_transposed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(WARPS * F2_WARP_BYTES + GSB_FWD_SMEM_PAD)));
     GSB_CUDA(cudaFuncSetAttribute(render_fwd_transposed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -630,6 +895,16 @@ int launch_render_fwd(const View& v, int P, const Geom* geom, const uint32_t* po
       render_fwd_transposed_kernel<false><<<T, WARPS * 32, smem2, st>>>(v, geom, point_list, ranges, tile_order, color,
                                                                         depth, alpha, n_contrib, final_T, nullptr, nullptr);
     GSB_POST_LAUNCH(debug, st, "render_fwd_transposed_kernel");
+    return GSB_OK;
+  }
+  if (variant == 3) {
+    if (hits && hit_count)
+      render_fwd_precull_kernel<true><<<T, WARPS * 32, smem_pc, st>>>(v, geom, point_list, ranges, tile_order, color,
+                                                                      depth, alpha, n_contrib, final_T, hits, hit_count);
+    else
+      render_fwd_precull_kernel<false><<<T, WARPS * 32, smem_pc, st>>>(v, geom, point_list, ranges, tile_order, color,
+                                                                       depth, alpha, n_contrib, final_T, nullptr, nullptr);
+    GSB_POST_LAUNCH(debug, st, "render_fwd_precull_kernel");
     return GSB_OK;
   }
   CUtensorMap tm;
