@@ -422,7 +422,7 @@ def stats() -> dict:
 
 
 BLEND_VARIANTS = {"native": 0, "standin": 1, "replay_bwd": 2, "rescan_bwd": 3, "rescan_packed_bwd": 4,
-                  "fwd_per_hit": 10, "fwd_transposed": 11}
+                  "fwd_per_hit": 10, "fwd_transposed": 11, "fwd_gather4": 12, "fwd_precull": 13}
 
 
 def set_blend_variant(name: str) -> None:
@@ -430,7 +430,9 @@ def set_blend_variant(name: str) -> None:
     them in two transposed phases, lane = pixel then lane = record), 'standin' (reference-STRUCTURE blend kernels of
     csrc/standin.cu, for measurement context and GPU cross-checks only), 'replay_bwd' (replays the records one hit per
     half-warp at a time with a shuffle butterfly), 'rescan_bwd' (the record-free round-1 backward that re-walks the
-    tile lists) or 'rescan_packed_bwd'; the last three are cross-checks of the default."""
+    tile lists) or 'rescan_packed_bwd'; the last three are cross-checks of the default.  'fwd_per_hit' (default) /
+    'fwd_transposed' / 'fwd_gather4' (TMA row gathers) / 'fwd_precull' (CTA-wide pre-cull) select the FORWARD blend
+    kernel only: measured alternatives that produce identical images, contributor counts and hit records."""
     _lib.check(_lib.load().gsb_set_blend_variant(BLEND_VARIANTS[name]), "gsb_set_blend_variant")
 
 
