@@ -265,6 +265,18 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
     const bool valid = idx < n;
     const uint32_t d = digit_of(key[r], shift);
     const uint32_t peers = match_digit(d, valid);
+#ifndef GSB_RADIX_RANK_NOBRANCH
+#define GSB_RADIX_RANK_NOBRANCH 1
+#endif
+#if GSB_RADIX_RANK_NOBRANCH
+    // every lane reads its digit's counter (peers read the same word: a broadcast), the lowest peer alone updates
+    // it: no divergent region and no shuffle of the old value in the hottest loop of the pass
+    const uint32_t old = s_cnt[warp][d];
+    __syncwarp();
+    if (valid && (peers & lt) == 0u) s_cnt[warp][d] = old + (uint32_t)__popc(peers);
+    rank[r] = old + (uint32_t)__popc(peers & lt);
+    __syncwarp();
+#else
     const int leader = valid ? __ffs(peers) - 1 : lane;
     uint32_t old = 0;
     if (valid && lane == leader) {
@@ -274,6 +286,7 @@ radix_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restri
     old = __shfl_sync(0xffffffffu, old, leader);
     rank[r] = old + (uint32_t)__popc(peers & lt);
     __syncwarp();
+#endif
   }
   RS_STAMP(2);
   __syncthreads();

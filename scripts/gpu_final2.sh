@@ -11,7 +11,7 @@ echo "bench rc $?"
 timeout 300 python bench.py --config vcr --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_vcr.json 2> gpurun_out/r2_bench_vcr.err
 timeout 300 python bench.py --config c3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c3.json 2> gpurun_out/r2_bench_c3.err
 timeout 300 python bench.py --config playback --steps 136 --warmup 8 --no-cpu-baseline > gpurun_out/r2_bench_playback.json 2> gpurun_out/r2_bench_playback.err
-timeout 300 python bench.py --impl reference --steps 4 --warmup 1 --cpu-budget-s 45 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err
+[ -n "$SKIP_REFERENCE" ] || timeout 300 python bench.py --impl reference --steps 4 --warmup 1 --cpu-budget-s 45 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.txt 2>&1; tail -1 gpurun_out/r2_smoke.txt
 python - <<'PY'
 import json
@@ -25,11 +25,11 @@ PY
 # ncu: launch list of a bench run (eager launches: ncu lists kernels launched from the host), then full captures
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-vcr --graph off > gpurun_out/r2_bench_under_ncu.log 2>&1
 echo "launch list rc $?"
-for k in render_fwd_kernel render_bwd_transposed_kernel preprocess_fwd_kernel preprocess_bwd_kernel radix_onesweep_kernel emit_kernel; do
+for k in ${NCU_KERNELS:-render_fwd_kernel render_bwd_transposed_kernel preprocess_fwd_kernel preprocess_bwd_kernel radix_onesweep_kernel emit_kernel}; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 12 -c 1 -o gpurun_out/r2_full_$k -f python scripts/perf_probe.py --iters 1 > gpurun_out/r2_ncu_$k.log 2>&1
   echo "$k rc $?"
 done
-GSB_FWD_VARIANT=gather4 timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_fwd_kernel -s 12 -c 1 -o gpurun_out/r2_full_render_fwd_gather4 -f python scripts/perf_probe.py --iters 1 > gpurun_out/r2_ncu_render_fwd_gather4.log 2>&1
+[ -n "$SKIP_GATHER4" ] || GSB_FWD_VARIANT=gather4 timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_fwd_kernel -s 12 -c 1 -o gpurun_out/r2_full_render_fwd_gather4 -f python scripts/perf_probe.py --iters 1 > gpurun_out/r2_ncu_render_fwd_gather4.log 2>&1
 echo "gather4 capture rc $?"
 for tool in memcheck racecheck initcheck; do
   timeout 900 compute-sanitizer --tool $tool --log-file gpurun_out/r2_sanitizer_$tool.log python scripts/sanitize_probe.py > gpurun_out/r2_sanitizer_$tool.out 2>&1
