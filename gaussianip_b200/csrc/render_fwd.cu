@@ -34,6 +34,13 @@ namespace gsb {
 namespace {
 
 constexpr int WARPS = 8;
+// GSB_FWD_NOBRANCH: 0 = per-slot `if (hit)` branches in the hit loop (rounds 1-2), 1 = the alpha evaluation of a
+// slot is branch-free, 2 (default) = the blend of a slot, the per-chunk cull test and the record store as well.  The
+// divergent regions cost far more than their instructions: r2y measured 222.8 -> 210.8 -> 195.3 us per view for
+// 0 / 1 / 2 with bit-identical results.
+#ifndef GSB_FWD_NOBRANCH
+#define GSB_FWD_NOBRANCH 2
+#endif
 #ifndef GSB_FWD_HB
 #define GSB_FWD_HB 2
 #endif
@@ -232,10 +239,12 @@ render_fwd_kernel(View v, const __grid_constant__ CUtensorMap geom_map, const Ge
 #if GSB_FWD_NOBRANCH >= 2
       {
         // branch-free: lanes past the end of the list test whatever their (unwritten) slot holds and are masked
-        const float4 a = rec0(lane);
+        // (the empty asm keeps the compiler from sinking the load back under a branch on `in_list`)
+        float4 a = rec0(lane);
+        asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w));
         const bool in_list = e < n;
-        hitA = in_list && (fabsf(a.x - cxA) <= a.z + hwxA) && (fabsf(a.y - cyA) <= a.w + hwyA);
-        hitB = in_list && (fabsf(a.x - cxB) <= a.z + hwxB) && (fabsf(a.y - cyB) <= a.w + hwyB);
+        hitA = in_list & (fabsf(a.x - cxA) <= a.z + hwxA) & (fabsf(a.y - cyA) <= a.w + hwyA);
+        hitB = in_list & (fabsf(a.x - cxB) <= a.z + hwxB) & (fabsf(a.y - cyB) <= a.w + hwyB);
       }
 #else
       if (e < n) {
@@ -265,12 +274,6 @@ render_fwd_kernel(View v, const __grid_constant__ CUtensorMap geom_map, const Ge
         float4 ff[HB];
 #pragma unroll
         for (int i = 0; i < HB; ++i) {
-// GSB_FWD_NOBRANCH: 0 = per-slot `if (hit)` branches (rounds 1-2), 1 = the alpha evaluation of a slot is
-// branch-free, 2 (default) = the blend of a slot as well.  The divergent branches cost far more than their
-// instructions: r2y measured 222.8 -> 210.8 -> 195.3 us per view for 0 / 1 / 2 with identical results.
-#ifndef GSB_FWD_NOBRANCH
-#define GSB_FWD_NOBRANCH 2
-#endif
 #if GSB_FWD_NOBRANCH
           {
             // branch-free: a half without a hit in this slot evaluates record 0 and discards the result
@@ -334,7 +337,16 @@ render_fwd_kernel(View v, const __grid_constant__ CUtensorMap geom_map, const Ge
         __syncwarp();
         const uint32_t m = s_mask[warp][0][lane] | s_mask[warp][1][lane];
         const uint32_t nz = __ballot_sync(0xffffffffu, m != 0u);
+#if GSB_FWD_NOBRANCH >= 2
+        {
+          // predicated store: the slot address is computed by every lane so that no divergent region is needed
+          uint2* slot = rec_base + (rec_n + __popc(nz & ((1u << lane) - 1u)));
+          asm volatile("" : "+l"(slot));
+          if (m) *slot = make_uint2(gid_cur, m);
+        }
+#else
         if (m) rec_base[rec_n + __popc(nz & ((1u << lane) - 1u))] = make_uint2(gid_cur, m);
+#endif
         rec_n += __popc(nz);
         gid_cur = gid_issued;
       }
