@@ -89,11 +89,11 @@ typedef struct GsbLayout {
   size_t saved_bytes_forward_only;
   size_t scratch_bytes;
   size_t off_rect;        /* P x {u16 minx,miny,maxx,maxy} */
-  size_t off_tiles;       /* P x u32  tiles_touched */
+  size_t off_tiles;       /* P x u32  tiles_touched (written by the forward; the emission derives counts from off_rect) */
   size_t off_dkeys0;               /* P x u32  depth keys (0xFFFFFFFF when culled), kept intact */
   size_t off_dkeys1, off_dkeys2;   /* P x u32  depth-sort ping/pong keys */
   size_t off_didx0, off_didx1;     /* P x u32  depth-sort ping/pong Gaussian ids */
-  size_t off_offsets;     /* P x u32  exclusive scan of tiles_touched in emission order */
+  size_t off_offsets;     /* P x u32  reserved (the exclusive scan lives in registers of the emission kernel) */
   size_t off_blocksums;   /* scan chain of the emission kernel (u64 words) */
   size_t off_hist;        /* radix per-block digit histograms + digit totals */
   size_t off_tkeys0, off_tkeys1;   /* D_cap x u32 tile ids ping/pong */
@@ -129,8 +129,11 @@ int gsb_preprocess_fwd(const GsbSettings* s, int P, int K,
  * identifyTileRanges.  Result: saved.point_list, saved.ranges, saved.counts.
  * Where the reference synchronises the device to read num_rendered, this library copies
  * saved.counts (8 x u32) to `host_counts` (pinned host memory, may be null) right after the
- * scan and records `event` (a cudaEvent_t, may be null) behind that copy: the host can wait on
- * the event alone, while the sort and blend kernels are already queued. */
+ * emission kernel (which scans the instance counts and publishes D) and records `event` (a
+ * cudaEvent_t, may be null) behind that copy: the host can wait on the event alone, while the
+ * sort and blend kernels are already queued.  Must follow gsb_preprocess_fwd of the same view on
+ * the same stream and scratch block (it consumes the tile rectangles, depth keys and the
+ * prefiltered flag that call left there). */
 int gsb_bin_sort(const GsbSettings* s, int P, void* saved, void* scratch, long long D_cap,
                  int mode, uint32_t* host_counts, void* event, void* stream);
 

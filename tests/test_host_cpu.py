@@ -86,6 +86,15 @@ def test_layout_is_consistent(lib):
     T = ((150 + 15) // 16) * ((100 + 15) // 16)
     assert L.off_n_contrib - L.off_ranges >= T * 8
     assert L.scratch_bytes > L.off_ggrad + 1000 * 48 - 1
+    # the emission kernel's scan chain (u64: ticket, flag, one word per 1024-Gaussian block and per group of 32
+    # blocks) and the sort's status words (blocks + groups of 32, 256 words each, per pass) fit their regions
+    for P, D in ((1, 1), (1000, 5000), (1_000_000, 2_200_000), (3_000_000, 1000), (5000, 9_000_000)):
+        Lb = _lib.layout(P, 64, 64, D)
+        blocks = (P + 1023) // 1024
+        assert Lb.off_hist - Lb.off_blocksums >= 8 * (2 + blocks + (blocks + 31) // 32), (P, D)
+        n = max(P, D)
+        nb = (n + 2047) // 2048
+        assert Lb.off_tkeys0 - Lb.off_hist >= 4 * (8 * 256 + 256 + 8 * (nb + (nb + 31) // 32) * 256), (P, D)
     # growth is monotone in every argument
     assert _lib.layout(2000, 100, 150, 5000).saved_bytes > L.saved_bytes
     assert _lib.layout(1000, 100, 150, 9000).scratch_bytes > L.scratch_bytes
