@@ -41,6 +41,19 @@ cudaEvent_t prof_get_event() {
 }
 }  // namespace
 
+int device_sm_count(int* sms) {
+  static std::atomic<int> cache[64];      // zero-initialised; index = device ordinal (mod 64)
+  int dev = 0;
+  GSB_CUDA(cudaGetDevice(&dev));
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
+  if (n == 0) {
+    GSB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev & 63].store(n, std::memory_order_relaxed);
+  }
+  *sms = n;
+  return GSB_OK;
+}
+
 void prof_begin(int stage, cudaStream_t st) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);

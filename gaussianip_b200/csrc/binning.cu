@@ -726,14 +726,8 @@ int launch_bin_sort(const View& v, int P, void* saved, void* scratch, const GsbL
   uint64_t* kB64 = at<uint64_t>(scratch, L.off_keys64_1);
   uint32_t* tvA = inA ? point_list : alt_vals;
   uint32_t* tvB = inA ? alt_vals : point_list;
-  static std::atomic<int> sm_count{0};
-  int sms = sm_count.load(std::memory_order_relaxed);
-  if (sms == 0) {
-    int dev = 0;
-    GSB_CUDA(cudaGetDevice(&dev));
-    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    sm_count.store(sms, std::memory_order_relaxed);
-  }
+  int sms = 0;
+  { const int rc_sm = device_sm_count(&sms); if (rc_sm) return rc_sm; }
   const int emit_grid = sc_blocks < sms * GSB_EMIT_MINB ? sc_blocks : sms * GSB_EMIT_MINB;
   GSB_CUDA(cudaMemsetAsync(chain, 0, emit_chain_words(sc_blocks) * sizeof(unsigned long long), st));
   // the prefiltered-violation flag of preprocess_fwd sits in the sort's counter row, which the next line zeroes

@@ -133,6 +133,8 @@ inline const T* at(const void* base, size_t off) {
 // error plumbing (api.cu)
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch();
+// number of SMs of the CURRENT device (cached per device; api.cu): persistent kernels size their grids with it
+int device_sm_count(int* sms);
 // stage timing (api.cu): no-ops unless gsb_profile_enable(1)
 void prof_begin(int stage, cudaStream_t st);
 void prof_end(int stage, cudaStream_t st);

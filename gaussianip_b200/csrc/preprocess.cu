@@ -262,14 +262,8 @@ int launch_preprocess_fwd(const View& v, int P, int K, const float* means3D, con
                           uint8_t* clamped, ushort4* rect, uint32_t* tiles, uint32_t* dkeys,
                           void* radix_tmp, bool debug, cudaStream_t st) {
   if (P == 0) return GSB_OK;
-  static std::atomic<int> sm_count{0};
-  int sms = sm_count.load(std::memory_order_relaxed);
-  if (sms == 0) {
-    int dev = 0;
-    GSB_CUDA(cudaGetDevice(&dev));
-    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    sm_count.store(sms, std::memory_order_relaxed);
-  }
+  int sms = 0;
+  { const int rc_sm = device_sm_count(&sms); if (rc_sm) return rc_sm; }
   const int chunks = (P + 255) / 256;
   const int grid = chunks < sms * PRE_CTAS_PER_SM ? chunks : sms * PRE_CTAS_PER_SM;
   // the kernel also accumulates the digit-0 histogram of the depth keys for the depth sort
